@@ -1,0 +1,103 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in this directory from the UNMODIFIED reference.
+
+Run in the build container only (needs ``/root/reference``; the GPU box has no copy):
+
+    python tests/golden/make_golden.py
+
+For each seeded synthetic set it imports the reference's own extractors from
+``/root/reference/src/features`` (and exec's ``scripts/train_v55_powerlaw.py:106-202`` for the
+script-level decline-model fits), runs them on the long-format DataFrame, and stores
+inputs + outputs as ``<name>.npz``.  ``multiband_gp`` cannot be run (it imports ``george``,
+absent here) so it has no golden -- see ``oracle/gp2d.py``.
+
+Nothing is copied from the reference: only its outputs are recorded.
+"""
+import io
+import contextlib
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(REF, "src"))
+
+from mallorn_astrophysics_b200 import schema                      # noqa: E402
+from mallorn_astrophysics_b200.synth import make_edge_table, make_table   # noqa: E402
+
+
+def reference_powerlaw_namespace():
+    """exec the self-contained function block of the v55 driver (its body needs Kaggle data)."""
+    with open(os.path.join(REF, "scripts", "train_v55_powerlaw.py")) as fh:
+        lines = fh.readlines()
+    block = "".join(lines[105:202])          # lines 106-202: models, fit_decline_models, extract_powerlaw_features
+    ns = {"np": np}
+    exec(compile(block, "train_v55_powerlaw.py[106:202]", "exec"), ns)
+    return ns
+
+
+def run_reference(table):
+    import pandas as pd
+    from features.statistical import extract_statistical_features
+    from features.colors import extract_color_features
+    from features.lightcurve_shape import extract_shape_features
+    from features.tde_physics import extract_tde_physics_features
+    from features.physics_based import extract_physics_features
+    from features.bazin_fitting import extract_bazin_features
+
+    lc = table.to_frame()
+    meta = table.metadata_frame()
+    ids = list(table.object_ids)
+    out = {}
+    sink = io.StringIO()
+    with contextlib.redirect_stdout(sink), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        frames = {
+            "statistical": extract_statistical_features(lc, ids),
+            "colors": extract_color_features(lc, ids),
+            "shape": extract_shape_features(lc, ids),
+            "tde": extract_tde_physics_features(lc, ids),
+            "physics": extract_physics_features(lc, meta, ids),
+            "bazin": extract_bazin_features(lc, ids),
+        }
+        ns = reference_powerlaw_namespace()
+        present = [i for i in ids if (lc["object_id"] == i).any()]
+        frames["powerlaw"] = pd.DataFrame([ns["extract_powerlaw_features"](i, lc) for i in present])
+    id_to_idx = {s: k for k, s in enumerate(ids)}
+    for name, df in frames.items():
+        cols = [c for c in df.columns if c != "object_id"]
+        want = schema.MODULE_COLUMNS[name]
+        # Column *sets* must match exactly.  The order matches too except for two reference
+        # quirks that depend on which object comes first (tde_physics.py:299-303 inserts
+        # alpha_late before residual on its short-band path; physics_based.py:128-129 omits
+        # r_sf_slope for a 3-4 point r band) -- rows are stored in schema order.
+        assert sorted(cols) == sorted(want), (name, set(cols) ^ set(want))
+        if name not in ("tde", "physics"):
+            assert cols == want, name
+        cols = want
+        if name == "statistical":
+            assert df.columns[0] == "object_id"
+        else:
+            assert df.columns[-1] == "object_id" or name == "powerlaw"
+        out[f"{name}_rows"] = df[cols].to_numpy(dtype=np.float64)
+        out[f"{name}_present"] = np.array([id_to_idx[s] for s in df["object_id"]], dtype=np.int64)
+    return out
+
+
+def save(name, table):
+    ref = run_reference(table)
+    path = os.path.join(HERE, f"{name}.npz")
+    np.savez_compressed(path, obj=table.obj, band=table.band, t=table.t, flux=table.flux, err=table.err,
+                        n_obj=np.int64(table.n_obj), z=table.z, ebv=table.ebv, **ref)
+    print(name, table.n_obj, "objects", table.n_rows, "rows ->", path, os.path.getsize(path) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    save("ref_sparse", make_table(48, config_index=0))
+    save("ref_dense", make_table(24, seed=424242, count_scale=2.5))
+    save("ref_edge", make_edge_table())
