@@ -1,0 +1,91 @@
+/* mallorn_b200.h -- C-ABI of libmallorn_b200.so (B200 / sm_100a light-curve featurisation).
+ *
+ * The reference (Smooth-Cactus0/MALLORN-astrophysics) is pure Python and has no FFI of its own;
+ * its boundary for this path is the set of batch extractors in src/features/.  Each entry point
+ * below is what the Python shim in mallorn_astrophysics_b200/features/ binds (ctypes) to serve
+ * the reference function named beside it.  Plain pointers and sizes only; every function
+ * returns 0 on success or a negative MLRN_E* code, with text from mlrn_last_error().  No C++
+ * exception crosses the boundary.  There is no CPU implementation behind any of these symbols.
+ *
+ * Pointers flagged by a *_on_device argument may be host or device memory; a `stream` argument
+ * is a cudaStream_t passed as void* (NULL = the legacy default stream).  With device outputs the
+ * calls are asynchronous on `stream`; with host outputs they return after the copy completes.
+ *
+ * Feature rows are float64, row-major [n_obj, n_cols], columns in the reference's order
+ * (mallorn_astrophysics_b200/schema.py).  One row per dense object index 0..n_obj-1; an object
+ * without observations yields the reference's "empty" values and is dropped by the shim
+ * (statistical.py:163-165).
+ */
+#ifndef MALLORN_B200_H
+#define MALLORN_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLRN_OK 0
+#define MLRN_EINVAL (-1)      /* bad argument */
+#define MLRN_ECUDA (-2)       /* CUDA runtime error (see mlrn_last_error) */
+#define MLRN_ETOOLONG (-3)    /* an object has more than MLRN_MAX_OBS observations */
+#define MLRN_ENODEVICE (-4)   /* no CUDA device: there is no CPU fallback */
+
+#define MLRN_MAX_OBS 1024     /* per-object observation cap (shared-memory staging) */
+#define MLRN_N_SEG 7          /* segments per object: u g r i z y + unknown filter */
+
+#define MLRN_STAT_COLS 123      /* extract_statistical_features   statistical.py:135      */
+#define MLRN_COLOR_COLS 83      /* extract_color_features         colors.py:347           */
+#define MLRN_SHAPE_COLS 65      /* extract_shape_features         lightcurve_shape.py:335 */
+#define MLRN_TDE_COLS 25        /* extract_tde_physics_features   tde_physics.py:377      */
+#define MLRN_PHYSICS_COLS 32    /* extract_physics_features       physics_based.py:461    */
+#define MLRN_BAZIN_COLS 52      /* extract_bazin_features         bazin_fitting.py:254    */
+#define MLRN_POWERLAW_COLS 27   /* extract_powerlaw_features      scripts/train_v55_powerlaw.py:196 */
+#define MLRN_GP2D_COLS 27       /* extract_multiband_gp_features  multiband_gp.py:347     */
+#define MLRN_SEGMETA_COLS 22    /* K1 integer outputs per object, see mlrn_store_segments */
+
+typedef struct mlrn_store mlrn_store;   /* packed, device-resident light curves of one batch */
+
+const char* mlrn_last_error(void);
+int mlrn_version(void);
+int mlrn_device_count(void);            /* number of CUDA devices (0 => every call fails) */
+
+/* K1 -- pack.  Replaces the per-extractor `lightcurves.groupby('object_id')` dict
+ * (statistical.py:155, colors.py:365, lightcurve_shape.py:353, physics_based.py:484,
+ * tde_physics.py:395, bazin_fitting.py:272, multiband_gp.py:369) and the per-band
+ * `obj_lc[obj_lc['Filter']==band].sort_values('Time (MJD)')` (lightcurve_shape.py:192 ...).
+ * Input: a flat long-format table in FILE order -- obj[i] = dense object index of row i
+ * (negative = skip the row), band[i] = 0..5 for u g r i z y, >= 6 for any other Filter.
+ * Builds CSR (object, band) segments ordered by (time, file rank) in HBM. */
+int mlrn_store_create(int device, int64_t n_rows, int32_t n_obj, const int32_t* obj, const uint8_t* band,
+                      const double* t, const double* flux, const double* err, int inputs_on_device,
+                      void* stream, mlrn_store** out);
+int mlrn_store_destroy(mlrn_store* s);
+/* rows kept, objects, and the largest per-object observation count */
+int mlrn_store_info(const mlrn_store* s, int64_t* n_rows, int32_t* n_obj, int32_t* max_obs);
+/* K1 integer outputs, int32 [n_obj, 22] to HOST memory: for each of the 7 segments
+ * {count, position of the first flux maximum in file order, same in time order} (-1 if empty),
+ * then peak_band (statistical.py:217-222).  Bit-exact contract. */
+int mlrn_store_segments(const mlrn_store* s, int32_t* out_host);
+/* packed columns to HOST memory (any pointer may be NULL): seg_off int64[n_obj*7+1],
+ * t/flux/err float64[n_rows], rank uint16[n_rows] */
+int mlrn_store_export(const mlrn_store* s, int64_t* seg_off, double* t, double* flux, double* err, uint16_t* rank);
+
+/* Feature passes.  out: float64 [n_obj, MLRN_*_COLS]. */
+int mlrn_stat(const mlrn_store* s, double* out, int out_on_device, void* stream);
+int mlrn_color(const mlrn_store* s, double* out, int out_on_device, void* stream);
+int mlrn_shape(const mlrn_store* s, double* out, int out_on_device, void* stream);
+int mlrn_tde(const mlrn_store* s, double* out, int out_on_device, void* stream);
+/* z: redshift per object (metadata['Z'], physics_based.py:481,496); NaN = unknown */
+int mlrn_physics(const mlrn_store* s, const double* z, int z_on_device, double* out, int out_on_device, void* stream);
+/* status (optional, may be NULL): int32 [n_obj, 6, 2] = {TRF termination status, nfev} per band;
+ * status < -99 means curve_fit would have raised (NaN row). */
+int mlrn_bazin(const mlrn_store* s, double* out, int32_t* status, int out_on_device, void* stream);
+/* status (optional): int32 [n_obj, 27, 2] */
+int mlrn_powerlaw(const mlrn_store* s, double* out, int32_t* status, int out_on_device, void* stream);
+/* status (optional): int32 [n_obj, 4] = {L-BFGS-B iterations, function evaluations, termination code, N used} */
+int mlrn_gp2d(const mlrn_store* s, double* out, int32_t* status, int out_on_device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MALLORN_B200_H */

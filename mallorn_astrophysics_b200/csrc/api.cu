@@ -1,0 +1,146 @@
+// api.cu -- the C-ABI of libmallorn_b200.so (include/mallorn_b200.h).  Thin: argument checks,
+// host<->device staging, stream plumbing.  All arithmetic lives in the kernels.
+#include <cuda_runtime.h>
+#include <string>
+#include <new>
+#include "store.cuh"
+#include "../../include/mallorn_b200.h"
+
+namespace mlrn {
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  cudaGetLastError();
+  return MLRN_ECUDA;
+}
+int pack_device(mlrn_store* s, int64_t n_rows, const int32_t* obj, const uint8_t* band, const double* t,
+                const double* flux, const double* err, cudaStream_t st);
+int run_stat(const mlrn_store* s, double* out_dev, cudaStream_t st);
+}  // namespace mlrn
+
+using mlrn::set_error;
+
+namespace {
+
+struct DevGuard {
+  int prev = -1;
+  explicit DevGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); }
+  ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// Runs `pass(out_dev)`; if the caller's buffer is host memory, stages through a device buffer.
+template <class F>
+int with_output(const mlrn_store* s, double* out, int out_on_device, int cols, cudaStream_t st, F pass) {
+  if (!s || !out) { set_error("null store or output"); return MLRN_EINVAL; }
+  DevGuard g(s->device);
+  const size_t bytes = sizeof(double) * (size_t)s->n_obj * cols;
+  if (out_on_device) return pass(out);
+  if (bytes == 0) return MLRN_OK;
+  double* d = nullptr;
+  MLRN_CUDA(cudaMallocAsync(&d, bytes, st));
+  int rc = pass(d);
+  if (rc == MLRN_OK) {
+    cudaError_t e = cudaMemcpyAsync(out, d, bytes, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = mlrn::cuda_fail(e, "copy of feature rows to host");
+  }
+  cudaFreeAsync(d, st);
+  return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mlrn_last_error(void) { return mlrn::g_err.c_str(); }
+int mlrn_version(void) { return 100; }
+int mlrn_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int mlrn_store_create(int device, int64_t n_rows, int32_t n_obj, const int32_t* obj, const uint8_t* band,
+                      const double* t, const double* flux, const double* err, int inputs_on_device,
+                      void* stream, mlrn_store** out) {
+  if (!out) { set_error("out is null"); return MLRN_EINVAL; }
+  *out = nullptr;
+  if (n_rows < 0 || n_obj < 0 || (n_rows > 0 && (!obj || !band || !t || !flux || !err))) {
+    set_error("bad sizes or null column"); return MLRN_EINVAL;
+  }
+  if (n_rows > 2147483647LL) { set_error("more than 2^31-1 rows in one batch"); return MLRN_EINVAL; }
+  int ndev = mlrn_device_count();
+  if (ndev == 0) { set_error("no CUDA device visible; libmallorn_b200 has no CPU fallback"); return MLRN_ENODEVICE; }
+  if (device < 0 || device >= ndev) { set_error("device index out of range"); return MLRN_EINVAL; }
+  DevGuard g(device);
+  cudaStream_t st = (cudaStream_t)stream;
+  mlrn_store* s = new (std::nothrow) mlrn_store();
+  if (!s) { set_error("out of host memory"); return MLRN_EINVAL; }
+  s->device = device; s->n_obj = n_obj;
+  cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device);
+  const int32_t* d_obj = obj; const uint8_t* d_band = band; const double *d_t = t, *d_f = flux, *d_e = err;
+  void* tmp[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  int rc = MLRN_OK;
+  if (!inputs_on_device && n_rows > 0) {
+    const size_t n = (size_t)n_rows;
+    const size_t sz[5] = {n * 4, n, n * 8, n * 8, n * 8};
+    const void* src[5] = {obj, band, t, flux, err};
+    for (int k = 0; k < 5 && rc == MLRN_OK; ++k) {
+      cudaError_t e = cudaMallocAsync(&tmp[k], sz[k], st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(tmp[k], src[k], sz[k], cudaMemcpyHostToDevice, st);
+      if (e != cudaSuccess) rc = mlrn::cuda_fail(e, "host->device copy of the input columns");
+    }
+    d_obj = (const int32_t*)tmp[0]; d_band = (const uint8_t*)tmp[1];
+    d_t = (const double*)tmp[2]; d_f = (const double*)tmp[3]; d_e = (const double*)tmp[4];
+  }
+  if (rc == MLRN_OK) rc = mlrn::pack_device(s, n_rows, d_obj, d_band, d_t, d_f, d_e, st);
+  for (int k = 0; k < 5; ++k) if (tmp[k]) cudaFreeAsync(tmp[k], st);
+  if (rc != MLRN_OK) { mlrn_store_destroy(s); return rc; }
+  *out = s;
+  return MLRN_OK;
+}
+
+int mlrn_store_destroy(mlrn_store* s) {
+  if (!s) return MLRN_OK;
+  DevGuard g(s->device);
+  cudaFree(s->seg_off); cudaFree(s->t); cudaFree(s->flux); cudaFree(s->err); cudaFree(s->rank); cudaFree(s->seg_meta);
+  delete s;
+  return MLRN_OK;
+}
+
+int mlrn_store_info(const mlrn_store* s, int64_t* n_rows, int32_t* n_obj, int32_t* max_obs) {
+  if (!s) { set_error("null store"); return MLRN_EINVAL; }
+  if (n_rows) *n_rows = s->n_rows;
+  if (n_obj) *n_obj = s->n_obj;
+  if (max_obs) *max_obs = s->max_obs;
+  return MLRN_OK;
+}
+
+int mlrn_store_segments(const mlrn_store* s, int32_t* out_host) {
+  if (!s || !out_host) { set_error("null argument"); return MLRN_EINVAL; }
+  DevGuard g(s->device);
+  MLRN_CUDA(cudaDeviceSynchronize());
+  MLRN_CUDA(cudaMemcpy(out_host, s->seg_meta, sizeof(int32_t) * (size_t)s->n_obj * MLRN_SEGMETA_COLS, cudaMemcpyDeviceToHost));
+  return MLRN_OK;
+}
+
+int mlrn_store_export(const mlrn_store* s, int64_t* seg_off, double* t, double* flux, double* err, uint16_t* rank) {
+  if (!s) { set_error("null store"); return MLRN_EINVAL; }
+  DevGuard g(s->device);
+  MLRN_CUDA(cudaDeviceSynchronize());
+  const size_t n = (size_t)s->n_rows;
+  if (seg_off) MLRN_CUDA(cudaMemcpy(seg_off, s->seg_off, sizeof(int64_t) * ((size_t)s->n_obj * MLRN_N_SEG + 1), cudaMemcpyDeviceToHost));
+  if (t && n) MLRN_CUDA(cudaMemcpy(t, s->t, 8 * n, cudaMemcpyDeviceToHost));
+  if (flux && n) MLRN_CUDA(cudaMemcpy(flux, s->flux, 8 * n, cudaMemcpyDeviceToHost));
+  if (err && n) MLRN_CUDA(cudaMemcpy(err, s->err, 8 * n, cudaMemcpyDeviceToHost));
+  if (rank && n) MLRN_CUDA(cudaMemcpy(rank, s->rank, 2 * n, cudaMemcpyDeviceToHost));
+  return MLRN_OK;
+}
+
+int mlrn_stat(const mlrn_store* s, double* out, int out_on_device, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  return with_output(s, out, out_on_device, MLRN_STAT_COLS, st, [&](double* d) { return mlrn::run_stat(s, d, st); });
+}
+
+}  // extern "C"

@@ -1,0 +1,75 @@
+// passes.cu -- warp-per-object feature passes over the packed store (K2 moment pass, K3 scalar
+// passes).  One warp stages one object's observations into its shared-memory slice with
+// coalesced loads, computes the module's row there, and writes the row back coalesced.
+// Grid = a multiple of the SM count; warps stride over objects.
+#include <cuda_runtime.h>
+#include "store.cuh"
+#include "stat.cuh"
+#include "../../include/mallorn_b200.h"
+
+namespace mlrn {
+namespace {
+
+constexpr int PASS_WARPS = 4;
+constexpr int ROW_CAP = 128;      // >= widest row (123)
+
+enum PassId { PASS_STAT = 0 };
+
+template <int PASS> struct PassTraits;
+template <> struct PassTraits<PASS_STAT> { static constexpr int cols = STAT_COLS; static constexpr int scratch = 2; };
+
+__host__ __device__ inline size_t pass_bytes_per_warp(int np, int n_scratch) {
+  return (size_t)np * (8 * 3 + 8 * n_scratch + 2) + ROW_CAP * 8;
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(PASS_WARPS * 32)
+k_pass(const long long* __restrict__ seg_off, const double* __restrict__ gt, const double* __restrict__ gf,
+       const double* __restrict__ ge, const unsigned short* __restrict__ grank, const double* __restrict__ z,
+       int n_obj, int np, double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int NS = PassTraits<PASS>::scratch;
+  constexpr int COLS = PassTraits<PASS>::cols;
+  WarpTeam tm;
+  const int warp = threadIdx.x >> 5;
+  unsigned char* base = smem + (size_t)warp * pass_bytes_per_warp(np, NS);
+  double* row = (double*)base;
+  double* st = row + ROW_CAP;
+  double* sf = st + np;
+  double* se = sf + np;
+  double* scr = se + np;
+  unsigned short* srank = (unsigned short*)(scr + (size_t)NS * np);
+
+  for (long long o = (long long)blockIdx.x * PASS_WARPS + warp; o < n_obj; o += (long long)gridDim.x * PASS_WARPS) {
+    ObjView v;
+    stage_object(tm, seg_off, gt, gf, ge, grank, o, st, sf, se, srank, v);
+    if (PASS == PASS_STAT) stat_row(tm, v, scr, scr + np, row);
+    tm.sync();
+    double* dst = out + o * COLS;
+    for (int k = tm.rank(); k < COLS; k += 32) dst[k] = row[k];
+    tm.sync();
+  }
+}
+
+template <int PASS>
+int launch_pass(const mlrn_store* s, const double* z, double* out, cudaStream_t st) {
+  if (s->n_obj == 0) return MLRN_OK;
+  const int np = next_pow2(s->max_obs > 1 ? s->max_obs : 1);
+  const size_t smem = pass_bytes_per_warp(np, PassTraits<PASS>::scratch) * PASS_WARPS;
+  MLRN_CUDA(cudaFuncSetAttribute(k_pass<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  MLRN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pass<PASS>, PASS_WARPS * 32, smem));
+  if (per_sm < 1) per_sm = 1;
+  long long want = ((long long)s->n_obj + PASS_WARPS - 1) / PASS_WARPS;
+  long long cap = (long long)s->sm_count * per_sm;
+  int grid = (int)(want < cap ? want : cap);
+  k_pass<PASS><<<grid, PASS_WARPS * 32, smem, st>>>(s->seg_off, s->t, s->flux, s->err, s->rank, z, s->n_obj, np, out);
+  MLRN_CUDA(cudaGetLastError());
+  return MLRN_OK;
+}
+
+}  // namespace
+
+int run_stat(const mlrn_store* s, double* out_dev, cudaStream_t st) { return launch_pass<PASS_STAT>(s, nullptr, out_dev, st); }
+
+}  // namespace mlrn

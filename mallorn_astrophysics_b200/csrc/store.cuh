@@ -1,0 +1,30 @@
+// store.cuh -- device-resident packed light-curve store (opaque `mlrn_store` of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+struct mlrn_store {
+  int device = 0;
+  int64_t n_rows = 0;       // rows kept (obj >= 0)
+  int32_t n_obj = 0;
+  int32_t max_obs = 0;      // largest per-object count
+  int32_t sm_count = 148;
+  long long* seg_off = nullptr;     // [n_obj*7 + 1]
+  double* t = nullptr;              // [n_rows]
+  double* flux = nullptr;
+  double* err = nullptr;
+  unsigned short* rank = nullptr;   // [n_rows]
+  int32_t* seg_meta = nullptr;      // [n_obj*22]
+};
+
+namespace mlrn {
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+}  // namespace mlrn
+
+#define MLRN_CUDA(call)                                                   \
+  do {                                                                    \
+    cudaError_t _e = (call);                                              \
+    if (_e != cudaSuccess) return mlrn::cuda_fail(_e, #call);             \
+  } while (0)

@@ -1,0 +1,57 @@
+"""Shared plumbing of the drop-in extractors: DataFrame in -> packed store -> CUDA pass -> DataFrame out.
+
+Schema conventions reproduced from the reference: one row per id of
+``object_ids`` in request order, ids without light-curve rows omitted
+(``src/features/statistical.py:163-165``), ``object_id`` first for the statistical frame and last
+for every other frame, float64 columns (``*_n_obs`` / ``peak_band`` integer), NaN for anything
+the reference could not compute.  Inputs are never mutated.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+
+from .. import schema
+from ..store import LightCurveStore
+
+
+def _request_index(ids, object_ids):
+    """positions in the unique-id table for every requested id (duplicates preserved)."""
+    import pandas as pd
+    return ids.get_indexer(pd.Series(list(object_ids), dtype=object))
+
+
+def run_frame_module(module: str, lightcurves, object_ids: Optional[Sequence] = None, metadata=None,
+                     device: int = 0):
+    import pandas as pd
+    if object_ids is None:
+        object_ids = lightcurves["object_id"].unique()
+    object_ids = list(object_ids)
+    store, ids = LightCurveStore.from_frame(lightcurves, object_ids, device=device)
+    try:
+        z = None
+        if module == "physics":
+            # z_lookup = dict(zip(metadata['object_id'], metadata['Z'])): the LAST duplicate wins
+            # (physics_based.py:481); ids missing from the metadata get NaN (:496)
+            zmap = pd.Series(metadata["Z"].to_numpy(dtype=np.float64), index=metadata["object_id"].to_numpy())
+            zmap = zmap[~zmap.index.duplicated(keep="last")]
+            z = zmap.reindex(ids).to_numpy(dtype=np.float64)
+        rows = store.features(module, z=z)
+        counts = store.segments()[:, 0:21:3].sum(axis=1)
+    finally:
+        store.close()
+    req = _request_index(ids, object_ids)
+    req = req[counts[req] > 0]                       # drop ids with no observations
+    cols = schema.MODULE_COLUMNS[module]
+    df = pd.DataFrame(rows[req], columns=cols)
+    id_col = np.asarray(ids, dtype=object)[req]
+    if module == "statistical":
+        for c in schema.STAT_INT_COLUMNS:
+            df[c] = df[c].astype(np.int64)
+        df.insert(0, "object_id", id_col)
+    elif module == "powerlaw":
+        df.insert(0, "object_id", id_col)            # train_v55_powerlaw.py:197
+    else:
+        df["object_id"] = id_col
+    return df

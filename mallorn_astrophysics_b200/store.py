@@ -1,0 +1,153 @@
+"""Host-side handle of the packed, device-resident light-curve store.
+
+``LightCurveStore`` owns one ``mlrn_store`` (C-ABI) -- the CSR (object, band) layout in HBM that
+replaces the ``groupby('object_id')`` dict each reference extractor rebuilds
+(``src/features/statistical.py:155`` and siblings).  Inputs may be numpy arrays (host; copied
+inside the call) or torch CUDA tensors (device-resident; no copy).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _native
+from .schema import BAND_CODE, UNKNOWN_BAND
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _ptr(x, dtype):
+    """(address, keepalive, on_device) for a numpy array or torch tensor of the given numpy dtype."""
+    if _is_torch(x):
+        import torch
+        want = {np.int32: torch.int32, np.uint8: torch.uint8, np.float64: torch.float64}[dtype]
+        if x.dtype != want or not x.is_contiguous():
+            x = x.to(want).contiguous()
+        return x.data_ptr(), x, x.is_cuda
+    a = np.ascontiguousarray(x, dtype=dtype)
+    return a.ctypes.data, a, False
+
+
+class LightCurveStore:
+    """Packed light curves of ``n_obj`` objects on one GPU."""
+
+    def __init__(self, obj, band, t, flux, err, n_obj: int, device: int = 0, stream: int = 0):
+        L = _native.lib()
+        _native.require_device()
+        n_rows = int(obj.shape[0])
+        ptrs = [_ptr(obj, np.int32), _ptr(band, np.uint8), _ptr(t, np.float64),
+                _ptr(flux, np.float64), _ptr(err, np.float64)]
+        on_dev = {p[2] for p in ptrs}
+        if len(on_dev) != 1:
+            raise ValueError("input columns must be all host arrays or all CUDA tensors")
+        self._h = C.c_void_p()
+        self.device, self.stream = int(device), int(stream)
+        rc = L.mlrn_store_create(self.device, n_rows, int(n_obj), *[p[0] for p in ptrs],
+                                 1 if on_dev.pop() else 0, self.stream, C.byref(self._h))
+        _native.check(rc, "mlrn_store_create")
+        nr, no, mo = C.c_int64(), C.c_int32(), C.c_int32()
+        _native.check(L.mlrn_store_info(self._h, C.byref(nr), C.byref(no), C.byref(mo)), "mlrn_store_info")
+        self.n_rows, self.n_obj, self.max_obs = nr.value, no.value, mo.value
+
+    # ------------------------------------------------------------------ construction helpers
+    @classmethod
+    def from_table(cls, table, device: int = 0, stream: int = 0) -> "LightCurveStore":
+        return cls(table.obj, table.band, table.t, table.flux, table.err, table.n_obj, device, stream)
+
+    @classmethod
+    def from_frame(cls, lightcurves, object_ids: Optional[Sequence] = None, device: int = 0, stream: int = 0):
+        """Factorise a reference-format DataFrame (``object_id, Time (MJD), Flux, Flux_err, Filter``).
+
+        Returns ``(store, ids)`` where ``ids`` are the unique requested ids in request order; rows
+        of other objects are skipped, as the reference's ``grouped.get(obj_id)`` never sees them.
+        """
+        import pandas as pd
+        if object_ids is None:
+            object_ids = lightcurves["object_id"].unique()
+        ids = pd.Index(pd.unique(pd.Series(list(object_ids), dtype=object)))
+        codes = ids.get_indexer(lightcurves["object_id"]).astype(np.int32)
+        band = lightcurves["Filter"].map(BAND_CODE).fillna(UNKNOWN_BAND).to_numpy(dtype=np.uint8)
+        store = cls(codes, band,
+                    lightcurves["Time (MJD)"].to_numpy(dtype=np.float64),
+                    lightcurves["Flux"].to_numpy(dtype=np.float64),
+                    lightcurves["Flux_err"].to_numpy(dtype=np.float64), len(ids), device, stream)
+        return store, ids
+
+    # ------------------------------------------------------------------ K1 outputs
+    def segments(self) -> np.ndarray:
+        """int32 [n_obj, 22]: per segment (count, file-order peak pos, time-order peak pos), peak_band."""
+        out = np.empty((self.n_obj, _native.SEGMETA_COLS), dtype=np.int32)
+        _native.check(_native.lib().mlrn_store_segments(self._h, out.ctypes.data), "mlrn_store_segments")
+        return out
+
+    def export(self) -> dict:
+        seg = np.empty(self.n_obj * _native.N_SEG + 1, dtype=np.int64)
+        t, f, e = (np.empty(self.n_rows, dtype=np.float64) for _ in range(3))
+        rank = np.empty(self.n_rows, dtype=np.uint16)
+        _native.check(_native.lib().mlrn_store_export(self._h, seg.ctypes.data, t.ctypes.data, f.ctypes.data,
+                                                      e.ctypes.data, rank.ctypes.data), "mlrn_store_export")
+        return {"seg_off": seg, "t": t, "flux": f, "err": e, "rank": rank}
+
+    def present(self) -> np.ndarray:
+        """Indices of objects that have at least one observation."""
+        return np.flatnonzero(self.segments()[:, 0:21:3].sum(axis=1) > 0)
+
+    # ------------------------------------------------------------------ feature passes
+    def features(self, module: str, z=None, out=None, status=None, stream: Optional[int] = None):
+        """Run one pass.  ``out``: None (returns a new numpy array), a numpy array, or a CUDA
+        tensor [n_obj, cols] float64 (asynchronous on ``stream``).  ``status``: optional int32
+        numpy array / CUDA tensor for the fit passes (see include/mallorn_b200.h)."""
+        L = _native.lib()
+        cols = _native.COLS[module]
+        st = self.stream if stream is None else int(stream)
+        ret = None
+        if out is None:
+            out = ret = np.empty((self.n_obj, cols), dtype=np.float64)
+        optr, okeep, odev = _ptr(out, np.float64)
+        if not _is_torch(out) and okeep is not out:
+            raise ValueError("out must be a C-contiguous float64 array")
+        if module == "physics":
+            if z is None:
+                z = np.full(self.n_obj, np.nan)
+            zptr, zkeep, zdev = _ptr(z, np.float64)
+            rc = L.mlrn_physics(self._h, zptr, 1 if zdev else 0, optr, 1 if odev else 0, st)
+        elif module in ("bazin", "powerlaw", "gp2d"):
+            sptr = 0
+            if status is not None:
+                if _is_torch(status):
+                    if status.is_cuda != odev:
+                        raise ValueError("status and out must live on the same side")
+                    sptr = status.data_ptr()
+                else:
+                    if odev or status.dtype != np.int32 or not status.flags.c_contiguous:
+                        raise ValueError("status must be a C-contiguous int32 array on the same side as out")
+                    sptr = status.ctypes.data
+            fn = getattr(L, {"bazin": "mlrn_bazin", "powerlaw": "mlrn_powerlaw", "gp2d": "mlrn_gp2d"}[module])
+            rc = fn(self._h, optr, sptr, 1 if odev else 0, st)
+        else:
+            fn = getattr(L, {"statistical": "mlrn_stat", "colors": "mlrn_color", "shape": "mlrn_shape",
+                             "tde": "mlrn_tde"}[module])
+            rc = fn(self._h, optr, 1 if odev else 0, st)
+        _native.check(rc, f"mlrn pass '{module}'")
+        return ret if ret is not None else out
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            _native.lib().mlrn_store_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

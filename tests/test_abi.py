@@ -1,0 +1,55 @@
+"""The C-ABI library must load and export every symbol include/mallorn_b200.h declares
+(no compute: this runs without a GPU)."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def native():
+    import __graft_entry__ as g
+    g.build()
+    from mallorn_astrophysics_b200 import _native
+    return _native
+
+
+def test_header_symbols_are_exported(native):
+    hdr = open(os.path.join(ROOT, "include", "mallorn_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(mlrn_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 10
+    L = native.lib()
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, f"declared in the header but not exported: {missing}"
+    assert L.mlrn_version() >= 100
+
+
+def test_no_cpu_fallback(native):
+    """Without a device the product path must fail loudly, not compute on the host."""
+    import numpy as np
+    if native.lib().mlrn_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    from mallorn_astrophysics_b200.store import LightCurveStore
+    with pytest.raises(native.MallornNativeError):
+        LightCurveStore(np.zeros(1, np.int32), np.zeros(1, np.uint8), np.zeros(1), np.zeros(1), np.ones(1), 1)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "mallorn_astrophysics_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "hostsim" not in src, f
+
+
+def test_schema_matches_header(native):
+    from mallorn_astrophysics_b200 import schema
+    hdr = open(os.path.join(ROOT, "include", "mallorn_b200.h")).read()
+    for mod, macro in (("statistical", "STAT"), ("colors", "COLOR"), ("shape", "SHAPE"), ("tde", "TDE"),
+                       ("physics", "PHYSICS"), ("bazin", "BAZIN"), ("powerlaw", "POWERLAW"), ("gp2d", "GP2D")):
+        n = int(re.search(rf"#define MLRN_{macro}_COLS (\d+)", hdr).group(1))
+        assert n == len(schema.MODULE_COLUMNS[mod]) == native.COLS[mod]
