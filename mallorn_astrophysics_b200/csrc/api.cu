@@ -17,6 +17,10 @@ int cuda_fail(cudaError_t e, const char* what) {
 int pack_device(mlrn_store* s, int64_t n_rows, const int32_t* obj, const uint8_t* band, const double* t,
                 const double* flux, const double* err, cudaStream_t st);
 int run_stat(const mlrn_store* s, double* out_dev, cudaStream_t st);
+int run_color(const mlrn_store* s, double* out_dev, cudaStream_t st);
+int run_shape(const mlrn_store* s, double* out_dev, cudaStream_t st);
+int run_tde(const mlrn_store* s, double* out_dev, cudaStream_t st);
+int run_physics(const mlrn_store* s, const double* z_dev, double* out_dev, cudaStream_t st);
 }  // namespace mlrn
 
 using mlrn::set_error;
@@ -141,6 +145,34 @@ int mlrn_store_export(const mlrn_store* s, int64_t* seg_off, double* t, double* 
 int mlrn_stat(const mlrn_store* s, double* out, int out_on_device, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   return with_output(s, out, out_on_device, MLRN_STAT_COLS, st, [&](double* d) { return mlrn::run_stat(s, d, st); });
+}
+
+int mlrn_color(const mlrn_store* s, double* out, int out_on_device, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  return with_output(s, out, out_on_device, MLRN_COLOR_COLS, st, [&](double* d) { return mlrn::run_color(s, d, st); });
+}
+int mlrn_shape(const mlrn_store* s, double* out, int out_on_device, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  return with_output(s, out, out_on_device, MLRN_SHAPE_COLS, st, [&](double* d) { return mlrn::run_shape(s, d, st); });
+}
+int mlrn_tde(const mlrn_store* s, double* out, int out_on_device, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  return with_output(s, out, out_on_device, MLRN_TDE_COLS, st, [&](double* d) { return mlrn::run_tde(s, d, st); });
+}
+int mlrn_physics(const mlrn_store* s, const double* z, int z_on_device, double* out, int out_on_device, void* stream) {
+  if (!s || !z) { set_error("null store or redshift column"); return MLRN_EINVAL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  DevGuard g(s->device);
+  const double* zd = z;
+  double* ztmp = nullptr;
+  if (!z_on_device && s->n_obj > 0) {
+    MLRN_CUDA(cudaMallocAsync(&ztmp, sizeof(double) * (size_t)s->n_obj, st));
+    MLRN_CUDA(cudaMemcpyAsync(ztmp, z, sizeof(double) * (size_t)s->n_obj, cudaMemcpyHostToDevice, st));
+    zd = ztmp;
+  }
+  int rc = with_output(s, out, out_on_device, MLRN_PHYSICS_COLS, st, [&](double* d) { return mlrn::run_physics(s, zd, d, st); });
+  if (ztmp) cudaFreeAsync(ztmp, st);
+  return rc;
 }
 
 }  // extern "C"

@@ -5,6 +5,10 @@
 #include <cuda_runtime.h>
 #include "store.cuh"
 #include "stat.cuh"
+#include "colors.cuh"
+#include "shape.cuh"
+#include "tde.cuh"
+#include "physics.cuh"
 #include "../../include/mallorn_b200.h"
 
 namespace mlrn {
@@ -13,10 +17,14 @@ namespace {
 constexpr int PASS_WARPS = 4;
 constexpr int ROW_CAP = 128;      // >= widest row (123)
 
-enum PassId { PASS_STAT = 0 };
+enum PassId { PASS_STAT = 0, PASS_COLOR, PASS_SHAPE, PASS_TDE, PASS_PHYSICS };
 
 template <int PASS> struct PassTraits;
 template <> struct PassTraits<PASS_STAT> { static constexpr int cols = STAT_COLS; static constexpr int scratch = 2; };
+template <> struct PassTraits<PASS_COLOR> { static constexpr int cols = COLOR_COLS; static constexpr int scratch = 2; };
+template <> struct PassTraits<PASS_SHAPE> { static constexpr int cols = SHAPE_COLS; static constexpr int scratch = 2; };
+template <> struct PassTraits<PASS_TDE> { static constexpr int cols = TDE_COLS; static constexpr int scratch = 4; };
+template <> struct PassTraits<PASS_PHYSICS> { static constexpr int cols = PHYSICS_COLS; static constexpr int scratch = 2; };
 
 __host__ __device__ inline size_t pass_bytes_per_warp(int np, int n_scratch) {
   return (size_t)np * (8 * 3 + 8 * n_scratch + 2) + ROW_CAP * 8;
@@ -44,6 +52,10 @@ k_pass(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
     ObjView v;
     stage_object(tm, seg_off, gt, gf, ge, grank, o, st, sf, se, srank, v);
     if (PASS == PASS_STAT) stat_row(tm, v, scr, scr + np, row);
+    if (PASS == PASS_COLOR) color_row(tm, v, scr, scr + np, row);
+    if (PASS == PASS_SHAPE) shape_row(tm, v, scr, scr + np, row);
+    if (PASS == PASS_TDE) tde_row(tm, v, scr, scr + np, scr + 2 * np, scr + 3 * np, row);
+    if (PASS == PASS_PHYSICS) physics_row(tm, v, z ? z[o] : qnan(), scr, scr + np, row);
     tm.sync();
     double* dst = out + o * COLS;
     for (int k = tm.rank(); k < COLS; k += 32) dst[k] = row[k];
@@ -54,7 +66,7 @@ k_pass(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
 template <int PASS>
 int launch_pass(const mlrn_store* s, const double* z, double* out, cudaStream_t st) {
   if (s->n_obj == 0) return MLRN_OK;
-  const int np = next_pow2(s->max_obs > 1 ? s->max_obs : 1);
+  const int np = next_pow2(s->max_obs > 64 ? s->max_obs : 64);   // scratch also holds small fixed tables
   const size_t smem = pass_bytes_per_warp(np, PassTraits<PASS>::scratch) * PASS_WARPS;
   MLRN_CUDA(cudaFuncSetAttribute(k_pass<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
@@ -71,5 +83,11 @@ int launch_pass(const mlrn_store* s, const double* z, double* out, cudaStream_t 
 }  // namespace
 
 int run_stat(const mlrn_store* s, double* out_dev, cudaStream_t st) { return launch_pass<PASS_STAT>(s, nullptr, out_dev, st); }
+int run_color(const mlrn_store* s, double* out_dev, cudaStream_t st) { return launch_pass<PASS_COLOR>(s, nullptr, out_dev, st); }
+int run_shape(const mlrn_store* s, double* out_dev, cudaStream_t st) { return launch_pass<PASS_SHAPE>(s, nullptr, out_dev, st); }
+int run_tde(const mlrn_store* s, double* out_dev, cudaStream_t st) { return launch_pass<PASS_TDE>(s, nullptr, out_dev, st); }
+int run_physics(const mlrn_store* s, const double* z_dev, double* out_dev, cudaStream_t st) {
+  return launch_pass<PASS_PHYSICS>(s, z_dev, out_dev, st);
+}
 
 }  // namespace mlrn

@@ -7,3 +7,6 @@ import these extractors unchanged; see INTEGRATION.md.  Re-exports mirror
 ``src/features/__init__.py:1-4``.
 """
 from .statistical import extract_statistical_features  # noqa: F401
+from .colors import extract_color_features  # noqa: F401
+from .lightcurve_shape import extract_shape_features  # noqa: F401
+from .physics_based import extract_physics_features  # noqa: F401

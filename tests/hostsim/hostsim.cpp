@@ -7,6 +7,10 @@
 #include <vector>
 #include <cstring>
 #include "stat.cuh"
+#include "colors.cuh"
+#include "shape.cuh"
+#include "tde.cuh"
+#include "physics.cuh"
 
 using namespace mlrn;
 
@@ -32,5 +36,26 @@ int hs_stat(long long n_obj, const long long* seg_off, const double* t, const do
   }
   return 0;
 }
+
+#define HS_PASS(NAME, COLS, CALL)                                                                        \
+  int NAME(long long n_obj, const long long* seg_off, const double* t, const double* f, const double* e,   \
+           const unsigned short* rank, const double* z, double* out) {                                     \
+    HostTeam tm;                                                                                           \
+    Scratch s(2 * MAX_OBS);                                                                                \
+    for (long long o = 0; o < n_obj; ++o) {                                                                \
+      ObjView v;                                                                                           \
+      stage_object(tm, seg_off, t, f, e, rank, o, s.t.data(), s.f.data(), s.e.data(), s.rank.data(), v);   \
+      double zz = z ? z[o] : qnan();                                                                       \
+      (void)zz;                                                                                            \
+      CALL;                                                                                                \
+      std::memcpy(out + o * COLS, s.row.data(), sizeof(double) * COLS);                                    \
+    }                                                                                                      \
+    return 0;                                                                                              \
+  }
+
+HS_PASS(hs_color, COLOR_COLS, color_row(tm, v, s.sa.data(), s.sb.data(), s.row.data()))
+HS_PASS(hs_shape, SHAPE_COLS, shape_row(tm, v, s.sa.data(), s.sb.data(), s.row.data()))
+HS_PASS(hs_tde, TDE_COLS, tde_row(tm, v, s.sa.data(), s.sb.data(), s.sc.data(), s.sd.data(), s.row.data()))
+HS_PASS(hs_physics, PHYSICS_COLS, physics_row(tm, v, zz, s.sa.data(), s.sb.data(), s.row.data()))
 
 }  // extern "C"

@@ -63,6 +63,35 @@ def test_statistical_matches_reference_golden(golden, fixture):
     assert np.array_equal(got[:, idx], want[:, idx])
 
 
+@pytest.mark.parametrize("module", ["colors", "shape", "tde", "physics"])
+@pytest.mark.parametrize("fixture", ["ref_sparse", "ref_dense", "ref_edge"])
+def test_scalar_passes_match_reference_golden(golden, fixture, module):
+    """K3 vs the unmodified reference's own output (rtol 1e-5; atol covers slopes that are 0 up to rounding)."""
+    g = golden[fixture]
+    with _store(g) as s:
+        got = s.features(module, z=g["z"])
+    present = g[f"{module}_present"]
+    got, want = got[present], g[f"{module}_rows"]
+    if fixture == "ref_edge":
+        keep = present != TIE_OBJECT
+        got, want = got[keep], want[keep]
+    _compare(got, want, rtol=1e-5, atol=1e-9, what=f"{module}/{fixture}")
+
+
+@pytest.mark.parametrize("module", ["colors", "shape", "tde", "physics"])
+def test_scalar_passes_match_oracle_at_scale(module):
+    from mallorn_astrophysics_b200.store import LightCurveStore
+    from mallorn_astrophysics_b200.synth import make_table
+    from oracle.extract import run_table
+    table = make_table(2048, config_index=2, count_scale=1.5)
+    with LightCurveStore.from_table(table) as s:
+        got = s.features(module, z=table.z)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        present, want = run_table(module, table)
+    _compare(got[present], want, rtol=1e-5, atol=1e-9, what=f"{module}/2048")
+
+
 def test_statistical_matches_oracle_at_scale():
     """4096 seeded objects against the oracle (seconds on the CPU side)."""
     from mallorn_astrophysics_b200.store import LightCurveStore
