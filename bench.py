@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- objects/s of the MALLORN light-curve featurisation on B200 (contract in the task statement).
+
+A *step* is one pass of the hot path over one batch of synthetic light curves: K1 pack (flat
+long-format rows -> CSR (object, band) segments in HBM) followed by every feature pass the
+library exports (statistical, colors, shape, tde_physics, physics_based, bazin, power-law,
+2-D GP), i.e. the full 434-column module table the v34a/v92d 222-feature set is selected from.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--objects M] [--impl reference]
+
+* ``value``  objects/s, inputs resident in HBM (flat columns on the device) when the clock starts.
+* ``e2e``    the same through the C-ABI with HOST buffers: H2D of the five input columns and D2H of
+             every feature table inside the timed region.
+* ``roofline`` the moment pass (north star: judged against HBM bandwidth), CUDA-event timed inside
+             the step; ``passes`` lists every pass's share of the step.
+* ``cpu_baseline`` the CPU oracle (``oracle/``: the reference's numpy/scipy arithmetic) on a bounded
+             sample of the same workload, all host cores.
+* ``--impl reference`` times only that CPU path (the reference has no GPU path and, being a Python
+             package with no native code, "the reference's own CPU implementation" is the oracle
+             restatement: ``/root/reference`` does not exist on the GPU box).
+
+N > 1: launched by torchrun, one rank per GPU; objects are sharded (weak scaling, fixed objects per
+GPU), no collective during compute, one NCCL all-gather of the feature table at the end of each step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+MODULES = ("statistical", "colors", "shape", "tde", "physics", "bazin", "powerlaw", "gp2d")
+METRIC = "light curves/sec for the 222-feature set (full 434-column module table)"
+UNIT = "objects/s"
+SEED = 20260118 + 3            # seed = 20260118 + config index (C4)
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks under load (B200_PROFILING.md "clocks line"), sampled through NVML while the timed region runs
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nv = None
+
+    def _run(self):
+        nv = self._nv
+        while not self._stop.wait(0.05):
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                for bit, name in self.REASONS.items():
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+
+    def __enter__(self):
+        if self._nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle over object chunks on all host cores
+# ----------------------------------------------------------------------------------------------
+def _cpu_chunk(args):
+    import warnings
+    from oracle.extract import run_module
+    cols, lo, hi, modules = args
+    keep = (cols["obj"] >= lo) & (cols["obj"] < hi)
+    obj = (cols["obj"][keep] - lo).astype(np.int32)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for m in modules:
+            run_module(m, obj, cols["band"][keep], cols["t"][keep], cols["flux"][keep], cols["err"][keep],
+                       hi - lo, cols["z"][lo:hi])
+    return hi - lo
+
+
+def cpu_rate(cols, n_objects, modules, cores):
+    """objects/s of the CPU oracle on the first ``n_objects`` objects, ``cores`` worker processes."""
+    import multiprocessing as mp
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    per = max(1, (n_objects + cores * 2 - 1) // (cores * 2))
+    jobs = [(cols, lo, min(lo + per, n_objects), modules) for lo in range(0, n_objects, per)]
+    t0 = time.perf_counter()
+    if cores == 1:
+        done = sum(_cpu_chunk(j) for j in jobs)
+    else:
+        with mp.get_context("fork").Pool(cores) as pool:
+            done = sum(pool.map(_cpu_chunk, jobs))
+    dt = time.perf_counter() - t0
+    return done / dt, dt
+
+
+def host_sample(n_objects):
+    from mallorn_astrophysics_b200.synth import make_table
+    tb = make_table(n_objects, seed=SEED)
+    return {"obj": tb.obj, "band": tb.band, "t": tb.t, "flux": tb.flux, "err": tb.err, "z": tb.z}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = args.cpu_objects or 16 * cores
+    cols = host_sample(per_step)
+    modules = list(MODULES)
+    for _ in range(args.warmup):
+        cpu_rate(cols, min(per_step, 2 * cores), modules, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_rate(cols, per_step, modules, cores)
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    sample = f"{per_step} objects/step of the C4 generator (seed {SEED}), {len(cols['obj'])} observations"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, per_step, modules),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_config(args, objects_per_gpu, modules):
+    return {"workload": "C4: 1M-object LSST-like synthetic set, full feature table (BASELINE.json configs[3])"
+            if objects_per_gpu == 1_000_000 else
+            f"C4 generator at {objects_per_gpu} objects per GPU (BASELINE.json configs[3] shape)",
+            "objects_per_gpu": objects_per_gpu, "bands": 6, "mean_obs_per_object": 150,
+            "modules": list(modules), "columns": 434,
+            "l2": "inputs larger than L2 (no flush needed)" if objects_per_gpu * 150 * 25 > 2 * 126e6 else
+                  "L2 flushed between steps",
+            "parallelism": f"objects sharded over {args.gpus} GPU(s), all-gather of the feature table"}
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def algorithmic_bytes(n_rows, n_obj):
+    """Moment pass, SURVEY.md 8(d) with this build's layout: one read of every observation
+    (t, flux, err float64 + uint16 file rank = 26 B), the 8 segment offsets of the object (int64) and one
+    write of the 123-column float64 row."""
+    return 26 * n_rows + n_obj * (8 * 8 + 123 * 8)
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from mallorn_astrophysics_b200 import _native
+    from mallorn_astrophysics_b200.store import LightCurveStore
+    from mallorn_astrophysics_b200.synth import make_columns_device
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _native.lib()
+    modules = [m for m in MODULES if hasattr(L, {"statistical": "mlrn_stat", "colors": "mlrn_color",
+               "shape": "mlrn_shape", "tde": "mlrn_tde", "physics": "mlrn_physics", "bazin": "mlrn_bazin",
+               "powerlaw": "mlrn_powerlaw", "gp2d": "mlrn_gp2d"}[m])]
+    if args.modules:
+        modules = [m for m in modules if m in args.modules.split(",")]
+    n_obj = args.objects
+    cols = make_columns_device(n_obj, SEED * 131 + rank, dev)
+    n_rows = int(cols["obj"].shape[0])
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+    outs = {m: torch.empty((n_obj, _native.COLS[m]), dtype=torch.float64, device=dev) for m in modules}
+    width = sum(_native.COLS[m] for m in modules)
+    table = torch.empty((n_obj, width), dtype=torch.float64, device=dev)
+    gathered = torch.empty((world * n_obj, width), dtype=torch.float64, device=dev) if world > 1 else None
+    flush = None
+    if n_rows * 25 < 2 * 126e6:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    pass_ms = {m: 0.0 for m in modules}
+    pass_ms["pack"] = 0.0
+    pass_ms["allgather"] = 0.0
+
+    def step(timed: bool):
+        marks = [("start", ev())]
+        marks[0][1].record(stream)
+        store = LightCurveStore(cols["obj"], cols["band"], cols["t"], cols["flux"], cols["err"], n_obj,
+                                device=local, stream=sptr)
+        e = ev(); e.record(stream); marks.append(("pack", e))
+        c0 = 0
+        for m in modules:
+            store.features(m, z=cols["z"] if m == "physics" else None, out=outs[m])
+            w = _native.COLS[m]
+            table[:, c0:c0 + w].copy_(outs[m])
+            c0 += w
+            e = ev(); e.record(stream); marks.append((m, e))
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, table)
+            e = ev(); e.record(stream); marks.append(("allgather", e))
+        stream.synchronize()
+        store.close()
+        if timed:
+            for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
+                pass_ms[name] += a.elapsed_time(b)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(False)
+    launches0 = L.mlrn_launch_count()
+    barrier()
+    with ClockSampler(local) as clk:
+        t_start, t_end = ev(), ev()
+        t_start.record(stream)
+        for _ in range(args.steps):
+            if flush is not None:
+                flush.zero_()
+            step(True)
+        t_end.record(stream)
+        barrier()
+    launches = L.mlrn_launch_count() - launches0
+    ms = t_start.elapsed_time(t_end)
+    if world > 1:
+        tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    value = world * n_obj * args.steps / (ms * 1e-3)
+
+    # ---- end to end: host buffers through the C-ABI, copies inside the timed region
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    host = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v) for k, v in cols.items()}
+    hnp = {k: v.numpy() for k, v in host.items()}
+    houts = {m: torch.empty((n_obj, _native.COLS[m]), dtype=torch.float64, pin_memory=True).numpy() for m in modules}
+    h2d = sum(hnp[k].nbytes for k in ("obj", "band", "t", "flux", "err")) + (hnp["z"].nbytes if "physics" in modules else 0)
+    d2h = sum(a.nbytes for a in houts.values())
+
+    def e2e_step():
+        store = LightCurveStore(hnp["obj"], hnp["band"], hnp["t"], hnp["flux"], hnp["err"], n_obj,
+                                device=local, stream=sptr)
+        for m in modules:
+            store.features(m, z=hnp["z"] if m == "physics" else None, out=houts[m])
+        store.close()
+
+    for _ in range(min(args.warmup, 3)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tms = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        e2e_s = float(tms.item())
+    e2e_value = world * n_obj * e2e_steps / e2e_s
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        stat_ms = pass_ms["statistical"] / args.steps if "statistical" in modules else None
+        roof = None
+        if stat_ms:
+            ach = algorithmic_bytes(n_rows, n_obj) / (stat_ms * 1e-3) / 1e9
+            roof = {"kernel": "k_pass<PASS_STAT> (moment pass)", "bound": "hbm", "achieved": ach, "peak": peak,
+                    "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s",
+                    "algorithmic_bytes_per_launch": algorithmic_bytes(n_rows, n_obj), "ms_per_launch": stat_ms}
+        cpu = None
+        if not args.no_cpu:
+            cores = os.cpu_count() or 1
+            n_cpu = args.cpu_objects or 8 * cores
+            sample_cols = host_sample(n_cpu)
+            rate, secs = cpu_rate(sample_cols, n_cpu, modules, cores)
+            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{n_cpu} objects of the same generator (seed {SEED}), modules {','.join(modules)}, "
+                             f"{secs:.1f} s on {cores} processes"}
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, n_obj, modules),
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": roof, "cpu_baseline": cpu,
+            "passes": {k: {"ms_per_step": v / args.steps, "share": v / ms} for k, v in pass_ms.items() if v > 0},
+            "observations_per_gpu": n_rows,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--objects", type=int, default=1_000_000, help="objects per GPU per step")
+    ap.add_argument("--modules", default="", help="comma list; default = every pass the library exports")
+    ap.add_argument("--cpu-objects", type=int, default=0, help="CPU sample size (default scales with host cores)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -48,6 +48,7 @@ typedef struct mlrn_store mlrn_store;   /* packed, device-resident light curves 
 const char* mlrn_last_error(void);
 int mlrn_version(void);
 int mlrn_device_count(void);            /* number of CUDA devices (0 => every call fails) */
+long long mlrn_launch_count(void);      /* kernels this library has launched so far in the process */
 
 /* K1 -- pack.  Replaces the per-extractor `lightcurves.groupby('object_id')` dict
  * (statistical.py:155, colors.py:365, lightcurve_shape.py:353, physics_based.py:484,

@@ -41,6 +41,7 @@ def lib() -> C.CDLL:
     L.mlrn_last_error.restype = C.c_char_p
     L.mlrn_version.restype = C.c_int
     L.mlrn_device_count.restype = C.c_int
+    L.mlrn_launch_count.restype = C.c_longlong
     L.mlrn_store_create.argtypes = [C.c_int, i64, i32, vp, vp, vp, vp, vp, C.c_int, vp, C.POINTER(vp)]
     L.mlrn_store_destroy.argtypes = [vp]
     L.mlrn_store_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]
@@ -54,8 +55,6 @@ def lib() -> C.CDLL:
     for name in ("mlrn_bazin", "mlrn_powerlaw", "mlrn_gp2d"):
         if hasattr(L, name):
             getattr(L, name).argtypes = [vp, vp, vp, C.c_int, vp]
-    for name in dir(L):
-        pass
     _lib = L
     return L
 

@@ -1,6 +1,7 @@
 // api.cu -- the C-ABI of libmallorn_b200.so (include/mallorn_b200.h).  Thin: argument checks,
 // host<->device staging, stream plumbing.  All arithmetic lives in the kernels.
 #include <cuda_runtime.h>
+#include <atomic>
 #include <string>
 #include <new>
 #include "store.cuh"
@@ -8,6 +9,8 @@
 
 namespace mlrn {
 static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 void set_error(const std::string& msg) { g_err = msg; }
 int cuda_fail(cudaError_t e, const char* what) {
   g_err = std::string(what) + ": " + cudaGetErrorString(e);
@@ -21,6 +24,9 @@ int run_color(const mlrn_store* s, double* out_dev, cudaStream_t st);
 int run_shape(const mlrn_store* s, double* out_dev, cudaStream_t st);
 int run_tde(const mlrn_store* s, double* out_dev, cudaStream_t st);
 int run_physics(const mlrn_store* s, const double* z_dev, double* out_dev, cudaStream_t st);
+int run_bazin(const mlrn_store* s, double* out_dev, int* status_dev, cudaStream_t st);
+int run_powerlaw(const mlrn_store* s, double* out_dev, int* status_dev, cudaStream_t st);
+int run_gp2d(const mlrn_store* s, double* out_dev, int* status_dev, cudaStream_t st);
 }  // namespace mlrn
 
 using mlrn::set_error;
@@ -53,12 +59,35 @@ int with_output(const mlrn_store* s, double* out, int out_on_device, int cols, c
   return rc;
 }
 
+// Same for a pass that also fills an optional int32 status table of `scols` values per object.
+template <class F>
+int with_status(const mlrn_store* s, double* out, int32_t* status, int out_on_device, int cols, int scols,
+                cudaStream_t st, F pass) {
+  if (!s) { set_error("null store"); return MLRN_EINVAL; }
+  if (out_on_device || !status)
+    return with_output(s, out, out_on_device, cols, st, [&](double* d) { return pass(d, status); });
+  DevGuard g(s->device);
+  const size_t sbytes = sizeof(int32_t) * (size_t)s->n_obj * scols;
+  if (sbytes == 0) return MLRN_OK;
+  int32_t* ds = nullptr;
+  MLRN_CUDA(cudaMallocAsync(&ds, sbytes, st));
+  int rc = with_output(s, out, 0, cols, st, [&](double* d) { return pass(d, ds); });
+  if (rc == MLRN_OK) {
+    cudaError_t e = cudaMemcpyAsync(status, ds, sbytes, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = mlrn::cuda_fail(e, "copy of the status table to host");
+  }
+  cudaFreeAsync(ds, st);
+  return rc;
+}
+
 }  // namespace
 
 extern "C" {
 
 const char* mlrn_last_error(void) { return mlrn::g_err.c_str(); }
 int mlrn_version(void) { return 100; }
+long long mlrn_launch_count(void) { return mlrn::g_launches.load(std::memory_order_relaxed); }
 int mlrn_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -108,7 +137,7 @@ int mlrn_store_create(int device, int64_t n_rows, int32_t n_obj, const int32_t* 
 int mlrn_store_destroy(mlrn_store* s) {
   if (!s) return MLRN_OK;
   DevGuard g(s->device);
-  cudaFree(s->seg_off); cudaFree(s->t); cudaFree(s->flux); cudaFree(s->err); cudaFree(s->rank); cudaFree(s->seg_meta);
+  cudaFree(s->seg_off); cudaFree(s->t); cudaFree(s->flux); cudaFree(s->err); cudaFree(s->rank); cudaFree(s->seg_meta); cudaFree(s->ticket);
   delete s;
   return MLRN_OK;
 }
@@ -173,6 +202,17 @@ int mlrn_physics(const mlrn_store* s, const double* z, int z_on_device, double* 
   int rc = with_output(s, out, out_on_device, MLRN_PHYSICS_COLS, st, [&](double* d) { return mlrn::run_physics(s, zd, d, st); });
   if (ztmp) cudaFreeAsync(ztmp, st);
   return rc;
+}
+
+int mlrn_bazin(const mlrn_store* s, double* out, int32_t* status, int out_on_device, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  return with_status(s, out, status, out_on_device, MLRN_BAZIN_COLS, 12, st,
+                     [&](double* d, int32_t* ds) { return mlrn::run_bazin(s, d, ds, st); });
+}
+int mlrn_powerlaw(const mlrn_store* s, double* out, int32_t* status, int out_on_device, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  return with_status(s, out, status, out_on_device, MLRN_POWERLAW_COLS, 54, st,
+                     [&](double* d, int32_t* ds) { return mlrn::run_powerlaw(s, d, ds, st); });
 }
 
 }  // extern "C"

@@ -49,13 +49,19 @@ __global__ void k_obj_partial(const int* __restrict__ seg_cnt, int n_obj, long l
                               int* __restrict__ max_obs) {
   __shared__ long long ws[SCAN_THREADS / 32];
   int64_t base = (int64_t)blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
-  long long s = 0; int mx = 0;
+  long long s = 0; int mx = 0, ms = 0;
   for (int k = 0; k < SCAN_ITEMS; ++k) {
     int64_t o = base + k;
-    if (o < n_obj) { int c = obj_total(seg_cnt, o); s += c; mx = max(mx, c); }
+    if (o < n_obj) {
+      int c = obj_total(seg_cnt, o); s += c; mx = max(mx, c);
+      for (int b = 0; b < N_SEG; ++b) ms = max(ms, seg_cnt[o * N_SEG + b]);
+    }
   }
-  for (int d = 16; d > 0; d >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, d); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d)); }
-  if ((threadIdx.x & 31) == 0) { ws[threadIdx.x >> 5] = s; atomicMax(max_obs, mx); }
+  for (int d = 16; d > 0; d >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, d); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    ms = max(ms, __shfl_xor_sync(0xffffffffu, ms, d));
+  }
+  if ((threadIdx.x & 31) == 0) { ws[threadIdx.x >> 5] = s; atomicMax(max_obs, mx); atomicMax(max_obs + 2, ms); }
   __syncthreads();
   if (threadIdx.x == 0) {
     long long tot = 0;
@@ -284,29 +290,32 @@ int pack_device(mlrn_store* s, int64_t n_rows, const int32_t* obj, const uint8_t
   MLRN_CUDA(cudaMallocAsync(&seg_cnt, sizeof(int) * (size_t)(n_seg > 0 ? n_seg : 1), st));
   MLRN_CUDA(cudaMallocAsync(&cursor, sizeof(int) * (size_t)(n_obj > 0 ? n_obj : 1), st));
   MLRN_CUDA(cudaMallocAsync(&partial, sizeof(long long) * (size_t)(n_blocks + 1), st));
-  MLRN_CUDA(cudaMallocAsync(&flags, sizeof(int) * 2, st));
+  MLRN_CUDA(cudaMallocAsync(&flags, sizeof(int) * 4, st));
   MLRN_CUDA(cudaMemsetAsync(seg_cnt, 0, sizeof(int) * (size_t)(n_seg > 0 ? n_seg : 1), st));
   MLRN_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int) * (size_t)(n_obj > 0 ? n_obj : 1), st));
-  MLRN_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 2, st));
+  MLRN_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 4, st));
   MLRN_CUDA(cudaMalloc(&s->seg_off, sizeof(long long) * (size_t)(n_seg + 1)));
   MLRN_CUDA(cudaMalloc(&s->seg_meta, sizeof(int32_t) * (size_t)(n_obj > 0 ? n_obj : 1) * MLRN_SEGMETA_COLS));
+  MLRN_CUDA(cudaMalloc(&s->ticket, sizeof(unsigned long long) * 4));
 
   const int row_grid = (int)((n_rows + 255) / 256 < (int64_t)s->sm_count * 16 ? (n_rows + 255) / 256 : (int64_t)s->sm_count * 16);
-  if (n_rows > 0) k_count<<<row_grid > 0 ? row_grid : 1, 256, 0, st>>>(obj, band, n_rows, n_obj, seg_cnt);
+  if (n_rows > 0) { k_count<<<row_grid > 0 ? row_grid : 1, 256, 0, st>>>(obj, band, n_rows, n_obj, seg_cnt); count_launch(); }
   if (n_obj > 0) {
     k_obj_partial<<<n_blocks, SCAN_THREADS, 0, st>>>(seg_cnt, n_obj, partial, flags);
     k_scan_partials<<<1, 1024, 0, st>>>(partial, n_blocks);
     k_obj_offsets<<<n_blocks, SCAN_THREADS, 0, st>>>(seg_cnt, n_obj, partial, s->seg_off);
+    count_launch(3);
   } else {
     MLRN_CUDA(cudaMemsetAsync(s->seg_off, 0, sizeof(long long), st));
   }
   MLRN_CUDA(cudaGetLastError());
-  long long total = 0; int h_flags[2] = {0, 0};
+  long long total = 0; int h_flags[4] = {0, 0, 0, 0};
   MLRN_CUDA(cudaMemcpyAsync(&total, s->seg_off + n_seg, sizeof(long long), cudaMemcpyDeviceToHost, st));
-  MLRN_CUDA(cudaMemcpyAsync(h_flags, flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+  MLRN_CUDA(cudaMemcpyAsync(h_flags, flags, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
   MLRN_CUDA(cudaStreamSynchronize(st));
   s->n_rows = total;
   s->max_obs = h_flags[0];
+  s->max_seg = h_flags[2];
   if (s->max_obs > MAX_OBS) {
     cudaFreeAsync(seg_cnt, st); cudaFreeAsync(cursor, st); cudaFreeAsync(partial, st); cudaFreeAsync(flags, st);
     set_error("an object has " + std::to_string(s->max_obs) + " observations; the per-object cap is " + std::to_string(MAX_OBS));
@@ -328,6 +337,7 @@ int pack_device(mlrn_store* s, int64_t n_rows, const int32_t* obj, const uint8_t
     if (grid > cap) grid = cap;
     k_arrange<<<grid, ARR_WARPS * 32, smem, st>>>(band, t, flux, err, rowid, s->seg_off, n_obj, np, s->t, s->flux,
                                                    s->err, s->rank, s->seg_meta, flags + 1);
+    count_launch(2);
   }
   MLRN_CUDA(cudaGetLastError());
   cudaFreeAsync(seg_cnt, st); cudaFreeAsync(cursor, st); cudaFreeAsync(partial, st); cudaFreeAsync(flags, st);

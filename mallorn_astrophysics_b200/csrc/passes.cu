@@ -77,6 +77,7 @@ int launch_pass(const mlrn_store* s, const double* z, double* out, cudaStream_t 
   int grid = (int)(want < cap ? want : cap);
   k_pass<PASS><<<grid, PASS_WARPS * 32, smem, st>>>(s->seg_off, s->t, s->flux, s->err, s->rank, z, s->n_obj, np, out);
   MLRN_CUDA(cudaGetLastError());
+  count_launch();
   return MLRN_OK;
 }
 

@@ -9,6 +9,7 @@ struct mlrn_store {
   int64_t n_rows = 0;       // rows kept (obj >= 0)
   int32_t n_obj = 0;
   int32_t max_obs = 0;      // largest per-object count
+  int32_t max_seg = 0;      // largest (object, band) segment
   int32_t sm_count = 148;
   long long* seg_off = nullptr;     // [n_obj*7 + 1]
   double* t = nullptr;              // [n_rows]
@@ -16,11 +17,13 @@ struct mlrn_store {
   double* err = nullptr;
   unsigned short* rank = nullptr;   // [n_rows]
   int32_t* seg_meta = nullptr;      // [n_obj*22]
+  unsigned long long* ticket = nullptr;   // [4] work counters of the fit / GP passes (one per pass)
 };
 
 namespace mlrn {
 void set_error(const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what);
+void count_launch(int n = 1);   // every kernel launch of the library is counted (mlrn_launch_count)
 }  // namespace mlrn
 
 #define MLRN_CUDA(call)                                                   \

@@ -17,6 +17,12 @@
 // is uniform across lanes.
 #pragma once
 #include "team.cuh"
+#if defined(TRF_TRACE) && !defined(__CUDACC__)
+#include <cstdio>
+#define TRF_LOG(...) std::printf(__VA_ARGS__)
+#else
+#define TRF_LOG(...) ((void)0)
+#endif
 
 namespace mlrn {
 
@@ -292,6 +298,7 @@ MLRN_FN int trf_bounded(const Team& tm, const Model& mdl, int m, double* x, cons
     double g_norm = 0.0;
     for (int i = 0; i < NP; ++i) g_norm = fmax(g_norm, fabs(g[i] * v[i]));
     if (g_norm < gtol) status = 1;
+    TRF_LOG("iter nfev %d cost %.10e gnorm %.6e Delta %.6e x0 %.17g x1 %.17g\n", nfev, cost, g_norm, Delta, x[0], x[1]);
     if (status != -1 || nfev == max_nfev) break;
     for (int i = 0; i < NP; ++i) { d[i] = sqrt(v[i]); diag_h[i] = g[i] * dv[i]; g_h[i] = d[i] * g[i]; }
     // ---- augmented scaled Jacobian -> Q (CGS2), R; then SVD of R
@@ -415,6 +422,7 @@ MLRN_FN int trf_bounded(const Team& tm, const Model& mdl, int m, double* x, cons
       double step_h_norm = vnorm<NP>(step_h);
       if (!finite) { Delta = 0.25 * step_h_norm; continue; }
       actual_reduction = cost - cost_new;
+      TRF_LOG("   trial nfev %d cost_new %.10e ared %.6e pred %.6e stepn %.6e alpha %.6e\n", nfev, cost_new, actual_reduction, predicted, step_h_norm, alpha);
       // update_tr_radius
       double ratio;
       if (predicted > 0.0) ratio = actual_reduction / predicted;
