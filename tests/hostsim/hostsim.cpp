@@ -12,6 +12,7 @@
 #include "tde.cuh"
 #include "physics.cuh"
 #include "fits.cuh"
+#include "gp_host.hpp"
 
 using namespace mlrn;
 
@@ -83,6 +84,18 @@ int hs_powerlaw(long long n_obj, const long long* seg_off, const double* t, cons
     stage_object(tm, seg_off, t, f, e, rank, o, s.t.data(), s.f.data(), s.e.data(), s.rank.data(), v);
     powerlaw_row(tm, v, s.sa.data(), s.sb.data(), work.data(), MAX_OBS, s.row.data(), status ? status + o * 54 : nullptr);
     std::memcpy(out + o * POWERLAW_COLS, s.row.data(), sizeof(double) * POWERLAW_COLS);
+  }
+  return 0;
+}
+
+int hs_gp2d(long long n_obj, const long long* seg_off, const double* t, const double* f, const double* e,
+            const unsigned short* rank, double* out, int* status) {
+  HostTeam tm;
+  Scratch s(2 * MAX_OBS);
+  for (long long o = 0; o < n_obj; ++o) {
+    ObjView v;
+    stage_object(tm, seg_off, t, f, e, rank, o, s.t.data(), s.f.data(), s.e.data(), s.rank.data(), v);
+    gphost::gp2d_row(v, out + o * 27, status ? status + o * 4 : nullptr);
   }
   return 0;
 }
