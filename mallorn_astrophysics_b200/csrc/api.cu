@@ -214,5 +214,10 @@ int mlrn_powerlaw(const mlrn_store* s, double* out, int32_t* status, int out_on_
   return with_status(s, out, status, out_on_device, MLRN_POWERLAW_COLS, 54, st,
                      [&](double* d, int32_t* ds) { return mlrn::run_powerlaw(s, d, ds, st); });
 }
+int mlrn_gp2d(const mlrn_store* s, double* out, int32_t* status, int out_on_device, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  return with_status(s, out, status, out_on_device, MLRN_GP2D_COLS, 4, st,
+                     [&](double* d, int32_t* ds) { return mlrn::run_gp2d(s, d, ds, st); });
+}
 
 }  // extern "C"

@@ -1,0 +1,483 @@
+// gp2d.cu -- K5: the 2-D (time x wavelength) Matern-3/2 GP features, one CTA per object.
+//
+// Reference: src/features/multiband_gp.py:34-344 (george GP + scipy L-BFGS-B); semantics of the absent
+// third-party package `george` as documented in oracle/gp2d.py (assumption A-george).  27 columns,
+// schema.GP2D_COLUMNS.
+//
+// Per object (N valid observations, N >= 10) the CTA holds the symmetric N x N matrix in shared memory as
+// lower-triangular 16 x 16 tiles (column-major inside a tile) and evaluates -ln L and its gradient with
+// an FP64 *tile sweep*: for each pivot tile k
+//     L = chol(A_kk)              (warp 0; ln|K| and the forward-substituted residual come from here, so
+//                                  -ln L has Cholesky accuracy)
+//     V_i = A_ik L^-T             (all other tile rows, column k read in place)
+//     A_ij -= V_i V_j^T           (every other tile: rank-16 update, 2 x 4 register blocks per lane)
+//     A_ik <- V_i L^-1, A_kk <- -(L L^T)^-1, b_i -= V_i w, b_k <- L^-T w      (w = L^-1 b_k)
+// which leaves -K^-1 in place and alpha = K^-1 r in b (symmetric block Gauss-Jordan with an augmented
+// right-hand side); the gradient 1/2 tr((alpha alpha^T - K^-1) dK/dtheta) is then an element-wise
+// contraction with the kernel derivatives recomputed on the fly.  N^3/2 FMA per evaluation, all in
+// shared memory; HBM traffic is one read of the object's observations and one 27-value row.
+// The hyper-parameter search is lbfgs4.cuh run redundantly by every thread on broadcast (f, g).
+// Objects with more than 16 * T_cap valid points (shared memory full) run in a second launch of the
+// same kernel with the tiles in a per-CTA global scratch (L2-resident).
+#include <cuda_runtime.h>
+#include "store.cuh"
+#include "objview.cuh"
+#include "lbfgs4.cuh"
+#include "../../include/mallorn_b200.h"
+
+namespace mlrn {
+namespace {
+
+constexpr int GP_THREADS = 512;
+constexpr int GP_WARPS = GP_THREADS / 32;
+constexpr int TB = 16;                 // tile edge
+constexpr int TT = TB * TB;            // doubles per tile
+constexpr int GP_COLS = 27;
+constexpr int T_SMEM_MAX = 13;         // 91 tiles + V buffer + vectors < 227 KB
+constexpr double GP_TINY = 1.25e-12;   // george's frozen white-noise floor
+constexpr double LOG_2PI = 1.8378770664093453;
+
+__device__ __constant__ double c_wave[6] = {3670.0, 4825.0, 6222.0, 7545.0, 8691.0, 9710.0};
+
+__host__ __device__ inline int n_tiles(int T) { return T * (T + 1) / 2; }
+__host__ __device__ inline size_t gp_fixed_doubles(int np) {
+  // vectors t, lam, y, noise, b (np each) + Lc, Li, LiT tiles + w[16] + reduction scratch
+  return 5 * (size_t)np + 3 * TT + TB + GP_WARPS * 4 + 16;
+}
+__host__ inline size_t gp_smem_bytes(int T, bool tiles_in_smem) {
+  size_t d = gp_fixed_doubles(T * TB);
+  if (tiles_in_smem) d += (size_t)(n_tiles(T) + T) * TT;
+  return d * sizeof(double) + 2 * n_tiles(T) + 64;      // + (I, J) byte table of the tiles
+}
+
+struct GpShared {
+  double *tiles, *vbuf;                 // [n_tiles][256], [T][256]
+  double *st, *sl, *sy, *sn, *sb;       // [np]
+  double *Lc, *Li, *LiT, *w, *red, *bc; // pivot factor, its inverse (row-major and transposed), scratch
+  unsigned char *tI, *tJ;
+};
+
+__device__ __forceinline__ double* tile_ptr(const GpShared& S, int I, int J) { return S.tiles + (size_t)(I * (I + 1) / 2 + J) * TT; }
+
+// deterministic block-wide sum of 4 values per thread; every thread gets the totals
+__device__ void block_sum4(const GpShared& S, double* v) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+  __syncthreads();
+  if (lane == 0) for (int q = 0; q < 4; ++q) S.red[warp * 4 + q] = v[q];
+  __syncthreads();
+  for (int q = 0; q < 4; ++q) { double s = 0.0; for (int w = 0; w < GP_WARPS; ++w) s += S.red[w * 4 + q]; v[q] = s; }
+}
+
+struct KernelPars { double mean, amp, m0, m1; };
+__device__ __forceinline__ KernelPars unpack(const double* p) {
+  KernelPars k; k.mean = p[0]; k.amp = 2.0 * exp(p[1]); k.m0 = exp(p[2]); k.m1 = exp(p[3]); return k;   // ndim * exp(log_constant)
+}
+
+// pivot tile: Cholesky, inverse, w = L^-1 b_k.  Executed by warp 0; lanes 0..15 own one row each.
+__device__ void pivot_warp(const GpShared& S, int k, double* quad, double* logdet, int* fail) {
+  const int lane = threadIdx.x & 31;
+  const double* A = tile_ptr(S, k, k);
+  double* L = S.Lc;                    // row-major L[r*16 + c]
+  for (int e = lane; e < TT; e += 32) { int r = e & 15, c = e >> 4; L[r * TB + c] = A[c * TB + r]; }
+  __syncwarp();
+  double ld = 0.0; bool bad = false;
+  for (int c = 0; c < TB; ++c) {
+    const double piv = L[c * TB + c];
+    if (!(piv > 0.0)) bad = true;
+    const double d = sqrt(piv);
+    ld += log(piv);                    // 2 ln L_cc
+    __syncwarp();
+    if (lane < TB && lane >= c) L[lane * TB + c] = (lane == c) ? d : L[lane * TB + c] / d;
+    __syncwarp();
+    if (lane < TB && lane > c) {
+      const double lrc = L[lane * TB + c];
+      for (int c2 = c + 1; c2 <= lane; ++c2) L[lane * TB + c2] -= lrc * L[c2 * TB + c];
+    }
+    __syncwarp();
+  }
+  // inverse: lane c (< 16) solves column c of L X = I
+  if (lane < TB) {
+    const int c = lane;
+    double x[TB];
+#pragma unroll
+    for (int r = 0; r < TB; ++r) {
+      double s = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+      for (int m = 0; m < TB; ++m) if (m < r) s -= L[r * TB + m] * ((m >= c) ? x[m] : 0.0);
+      x[r] = (r >= c) ? s / L[r * TB + r] : 0.0;
+    }
+#pragma unroll
+    for (int r = 0; r < TB; ++r) { S.Li[r * TB + c] = x[r]; S.LiT[c * TB + r] = x[r]; }
+  }
+  __syncwarp();
+  double wq = 0.0;
+  if (lane < TB) {
+    double s = 0.0;
+    for (int c = 0; c <= lane; ++c) s += S.Li[lane * TB + c] * S.sb[k * TB + c];
+    S.w[lane] = s; wq = s * s;
+  }
+  for (int o = 16; o > 0; o >>= 1) wq += __shfl_xor_sync(0xffffffffu, wq, o);
+  if (lane == 0) { *quad += wq; *logdet += ld; if (bad || !(ld == ld)) *fail = 1; }
+}
+
+// C(16x16, column-major) -= Vi Vj^T, one warp; lane (g = lane/4, h = lane%4) owns rows 2g..2g+1, cols 4h..4h+3
+__device__ __forceinline__ void tile_update(double* __restrict__ C, const double* __restrict__ Vi, const double* __restrict__ Vj) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, h = lane & 3;
+  double acc[2][4] = {};
+#pragma unroll
+  for (int m = 0; m < TB; ++m) {
+    const double2 a = *reinterpret_cast<const double2*>(Vi + m * TB + 2 * g);
+    const double2 b0 = *reinterpret_cast<const double2*>(Vj + m * TB + 4 * h);
+    const double2 b1 = *reinterpret_cast<const double2*>(Vj + m * TB + 4 * h + 2);
+    acc[0][0] += a.x * b0.x; acc[0][1] += a.x * b0.y; acc[0][2] += a.x * b1.x; acc[0][3] += a.x * b1.y;
+    acc[1][0] += a.y * b0.x; acc[1][1] += a.y * b0.y; acc[1][2] += a.y * b1.x; acc[1][3] += a.y * b1.y;
+  }
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    double2* p = reinterpret_cast<double2*>(C + (4 * h + cc) * TB + 2 * g);
+    double2 v = *p;
+    v.x -= acc[0][cc]; v.y -= acc[1][cc];
+    *p = v;
+  }
+}
+
+// -ln L and its gradient at p.  Leaves alpha in S.sb[0..n).  Result broadcast to every thread.
+__device__ void gp_eval(const GpShared& S, int n, int T, const double* p, double& f, double* grad) {
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const KernelPars kp = unpack(p);
+  const int nt = n_tiles(T);
+  // ---- (a) kernel matrix, b = y - mean
+  for (int e = tid; e < nt * TT; e += GP_THREADS) {
+    const int tl = e >> 8, r = e & 15, c = (e >> 4) & 15;
+    const int gi = S.tI[tl] * TB + r, gj = S.tJ[tl] * TB + c;
+    double v;
+    if (gi >= n || gj >= n) v = (gi == gj) ? 1.0 : 0.0;
+    else {
+      const double dt = S.st[gi] - S.st[gj], dl = S.sl[gi] - S.sl[gj];
+      const double s = sqrt(3.0 * (dt * dt / kp.m0 + dl * dl / kp.m1));
+      v = kp.amp * (1.0 + s) * exp(-s);
+      if (gi == gj) v += S.sn[gi];
+    }
+    S.tiles[e] = v;
+  }
+  for (int i = tid; i < T * TB; i += GP_THREADS) S.sb[i] = (i < n) ? S.sy[i] - kp.mean : 0.0;
+  double quad = 0.0, logdet = 0.0; int fail = 0;      // meaningful in warp 0 / lane 0 only
+  __syncthreads();
+  // ---- (b) tile sweep
+  for (int k = 0; k < T; ++k) {
+    if (warp == 0) pivot_warp(S, k, &quad, &logdet, &fail);
+    __syncthreads();
+    // V_i = X_i Li^T for i != k
+    for (int e = tid; e < (T - 1) * TT; e += GP_THREADS) {
+      int i = e >> 8; if (i >= k) ++i;
+      const int q = e & 255;
+      double s = 0.0;
+      if (i > k) {
+        const int r = q & 15, c = q >> 4;
+        const double* X = tile_ptr(S, i, k);
+        for (int m = 0; m <= c; ++m) s += X[m * TB + r] * S.Li[c * TB + m];
+        S.vbuf[i * TT + c * TB + r] = s;
+      } else {
+        const int c = q & 15, r = q >> 4;
+        const double* X = tile_ptr(S, k, i);          // X_i = tile(k, i)^T
+        for (int m = 0; m <= c; ++m) s += X[r * TB + m] * S.LiT[m * TB + c];
+        S.vbuf[i * TT + c * TB + r] = s;
+      }
+    }
+    __syncthreads();
+    // rank-16 updates of every tile outside row/column k (warp per tile)
+    {
+      const int Tm = T - 1, ntask = Tm * (Tm + 1) / 2;
+      for (int task = warp; task < ntask; task += GP_WARPS) {
+        int ii = (int)((sqrt(8.0 * task + 1.0) - 1.0) * 0.5);
+        while (ii * (ii + 1) / 2 > task) --ii;
+        while ((ii + 1) * (ii + 2) / 2 <= task) ++ii;
+        int jj = task - ii * (ii + 1) / 2;
+        const int i = ii + (ii >= k), j = jj + (jj >= k);
+        tile_update(tile_ptr(S, i, j), S.vbuf + i * TT, S.vbuf + j * TT);
+      }
+    }
+    // column k <- V_i Li (i != k); pivot tile <- -(Li^T Li); b updates.  Disjoint from the updates above.
+    for (int e = tid; e < (T - 1) * TT; e += GP_THREADS) {
+      int i = e >> 8; if (i >= k) ++i;
+      const int q = e & 255;
+      const double* V = S.vbuf + i * TT;
+      double s = 0.0;
+      if (i > k) {
+        const int r = q & 15, c = q >> 4;
+        for (int m = c; m < TB; ++m) s += V[m * TB + r] * S.Li[m * TB + c];
+        tile_ptr(S, i, k)[c * TB + r] = s;
+      } else {
+        const int c = q & 15, r = q >> 4;
+        for (int m = c; m < TB; ++m) s += V[m * TB + r] * S.Li[m * TB + c];
+        tile_ptr(S, k, i)[r * TB + c] = s;            // transposed store
+      }
+    }
+    for (int e = tid; e < TT; e += GP_THREADS) {
+      const int r = e & 15, c = e >> 4;
+      double s = 0.0;
+      for (int m = (r > c ? r : c); m < TB; ++m) s += S.LiT[r * TB + m] * S.LiT[c * TB + m];
+      tile_ptr(S, k, k)[c * TB + r] = -s;
+    }
+    for (int i = tid; i < T * TB; i += GP_THREADS) {
+      const int ti = i >> 4, r = i & 15;
+      if (ti != k) {
+        const double* V = S.vbuf + ti * TT;
+        double s = 0.0;
+        for (int m = 0; m < TB; ++m) s += V[m * TB + r] * S.w[m];
+        S.sb[i] -= s;
+      }
+    }
+    __syncthreads();
+    if (tid < TB) {                                   // b_k <- Li^T w  (after every reader of the old b_k / w)
+      double s = 0.0;
+      for (int m = tid; m < TB; ++m) s += S.Li[m * TB + tid] * S.w[m];
+      S.sb[k * TB + tid] = s;
+    }
+  }
+  __syncthreads();
+  // ---- (c) gradient contraction: 1/2 sum (alpha_i alpha_j - Kinv_ij) dK_ij ; tiles hold -Kinv
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int i = tid; i < n; i += GP_THREADS) acc[0] += S.sb[i];
+  for (int e = tid; e < nt * TT; e += GP_THREADS) {
+    const int tl = e >> 8, r = e & 15, c = (e >> 4) & 15;
+    const int I = S.tI[tl], J = S.tJ[tl];
+    const int gi = I * TB + r, gj = J * TB + c;
+    if (gi < n && gj < n) {
+      const double wgt = (I == J) ? 1.0 : 2.0;
+      const double Aij = wgt * (S.sb[gi] * S.sb[gj] + S.tiles[e]);
+      const double dt = S.st[gi] - S.st[gj], dl = S.sl[gi] - S.sl[gj];
+      const double a0 = dt * dt / kp.m0, a1 = dl * dl / kp.m1;
+      const double s = sqrt(3.0 * (a0 + a1)), ex = exp(-s);
+      const double dk = 1.5 * kp.amp * ex;
+      acc[1] += Aij * kp.amp * (1.0 + s) * ex; acc[2] += Aij * dk * a0; acc[3] += Aij * dk * a1;
+    }
+  }
+  if (tid == 0) { S.bc[0] = quad; S.bc[1] = logdet; S.bc[2] = (double)fail; }
+  block_sum4(S, acc);                                 // contains the barriers that publish bc[]
+  const double ll = -0.5 * S.bc[0] - 0.5 * S.bc[1] - 0.5 * (double)n * LOG_2PI;
+  if (S.bc[2] != 0.0 || !is_finite(ll)) {             // multiband_gp.py:141-154: 1e25 and a zero gradient
+    f = 1e25; grad[0] = grad[1] = grad[2] = grad[3] = 0.0;
+  } else {
+    f = -ll; grad[0] = -acc[0]; grad[1] = -0.5 * acc[1]; grad[2] = -0.5 * acc[2]; grad[3] = -0.5 * acc[3];
+  }
+  __syncthreads();
+}
+
+template <bool SMEM_TILES>
+__global__ void __launch_bounds__(GP_THREADS, 1)
+k_gp2d(const long long* __restrict__ seg_off, const double* __restrict__ gt, const double* __restrict__ gf,
+       const double* __restrict__ ge, const unsigned short* __restrict__ grank, int n_obj, int T_cap, int n_lo,
+       int n_hi, double* __restrict__ gscratch, unsigned long long* __restrict__ ticket, double* __restrict__ out,
+       int* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ long long s_obj;
+  __shared__ int s_cnt[GP_WARPS + 1];
+  __shared__ int s_pk;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int np_cap = T_cap * TB;
+  GpShared S;
+  {
+    double* d = (double*)smem_raw;
+    S.st = d; d += np_cap; S.sl = d; d += np_cap; S.sy = d; d += np_cap; S.sn = d; d += np_cap; S.sb = d; d += np_cap;
+    S.Lc = d; d += TT; S.Li = d; d += TT; S.LiT = d; d += TT; S.w = d; d += TB; S.red = d; d += GP_WARPS * 4; S.bc = d; d += 16;
+    if (SMEM_TILES) { S.tiles = d; d += (size_t)n_tiles(T_cap) * TT; S.vbuf = d; d += (size_t)T_cap * TT; }
+    else { S.tiles = gscratch + (size_t)blockIdx.x * (n_tiles(T_cap) + T_cap) * TT; S.vbuf = S.tiles + (size_t)n_tiles(T_cap) * TT; }
+    S.tI = (unsigned char*)d; S.tJ = S.tI + n_tiles(T_cap);
+  }
+  for (int tl = tid; tl < n_tiles(T_cap); tl += GP_THREADS) {
+    int I = (int)((sqrt(8.0 * tl + 1.0) - 1.0) * 0.5);
+    while (I * (I + 1) / 2 > tl) --I;
+    while ((I + 1) * (I + 2) / 2 <= tl) ++I;
+    S.tI[tl] = (unsigned char)I; S.tJ[tl] = (unsigned char)(tl - I * (I + 1) / 2);
+  }
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_obj = (long long)atomicAdd(ticket, 1ULL);
+    __syncthreads();
+    const long long o = s_obj;
+    if (o >= n_obj) break;
+    const long long* so = seg_off + o * N_SEG;
+    const long long base = so[0];
+    const int ntot = (int)(so[N_SEG] - base);
+    int off[N_SEG + 1];
+#pragma unroll
+    for (int b = 0; b <= N_SEG; ++b) off[b] = (int)(so[b] - base);
+    // ---- valid rows (multiband_gp.py:49-63), ordered compaction into shared memory
+    int n = 0;
+    double tmin_all = pinf();
+    for (int chunk = 0; chunk < ntot; chunk += GP_THREADS) {
+      const int i = chunk + tid;
+      bool keep = false; double t = 0.0, f = 0.0, e = 0.0; int b = 0;
+      if (i < ntot) {
+        t = gt[base + i]; f = gf[base + i]; e = ge[base + i];
+        while (b < N_SEG - 1 && i >= off[b + 1]) ++b;
+        tmin_all = fmin(tmin_all, t);
+        keep = (b < N_BAND) && !is_nan(f) && !is_nan(e) && (e > 0.0);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (lane == 0) s_cnt[warp] = __popc(m);
+      __syncthreads();
+      int before = n;
+      for (int w = 0; w < warp; ++w) before += s_cnt[w];
+      int total = 0;
+      for (int w = 0; w < GP_WARPS; ++w) total += s_cnt[w];
+      const int slot = before + __popc(m & ((1u << lane) - 1u));
+      if (keep && slot < np_cap) { S.st[slot] = t; S.sl[slot] = c_wave[b]; S.sy[slot] = f; S.sn[slot] = e; }
+      n += total;
+      __syncthreads();
+    }
+    double* row = out + o * GP_COLS;
+    const bool mine = (n >= n_lo && n <= n_hi);         // this launch's share (n < 10 rows belong to the first launch)
+    if (!mine) continue;
+    if (status && tid < 4) status[o * 4 + tid] = (tid == 3) ? n : 0;
+    if (n < 10) { if (tid < GP_COLS) row[tid] = qnan(); continue; }       // :66
+    // ---- t -= min(t); flux scale = median |f| over f != 0 (rank counting); y, noise; mean / var
+    double red[4] = {0.0, 0.0, 0.0, 0.0};
+    {
+      double tm = pinf();
+      for (int i = tid; i < n; i += GP_THREADS) tm = fmin(tm, S.st[i]);
+      for (int o2 = 16; o2 > 0; o2 >>= 1) { tm = fmin(tm, __shfl_xor_sync(0xffffffffu, tm, o2)); tmin_all = fmin(tmin_all, __shfl_xor_sync(0xffffffffu, tmin_all, o2)); }
+      __syncthreads();
+      if (lane == 0) { S.red[warp * 4] = tm; S.red[warp * 4 + 1] = tmin_all; }
+      __syncthreads();
+      tm = pinf(); tmin_all = pinf();
+      for (int w = 0; w < GP_WARPS; ++w) { tm = fmin(tm, S.red[w * 4]); tmin_all = fmin(tmin_all, S.red[w * 4 + 1]); }
+      __syncthreads();
+      for (int i = tid; i < n; i += GP_THREADS) S.st[i] -= tm;
+    }
+    int nz = 0;
+    for (int i = 0; i < n; ++i) nz += (S.sy[i] != 0.0);               // uniform; n is small
+    if (tid == 0) { S.bc[4] = qnan(); S.bc[5] = qnan(); }
+    __syncthreads();
+    for (int i = tid; i < n; i += GP_THREADS) {
+      const double vi = fabs(S.sy[i]);
+      if (S.sy[i] == 0.0) continue;
+      int rk = 0;
+      for (int j = 0; j < n; ++j) { const double vj = fabs(S.sy[j]); rk += (S.sy[j] != 0.0) && (vj < vi || (vj == vi && j < i)); }
+      if (rk == (nz >> 1)) S.bc[4] = vi;
+      if (rk == (nz >> 1) - 1) S.bc[5] = vi;
+    }
+    __syncthreads();
+    double scale = (nz == 0) ? qnan() : ((nz & 1) ? S.bc[4] : 0.5 * (S.bc[4] + S.bc[5]));   // numpy.median
+    if (scale == 0.0) scale = 1.0;
+    __syncthreads();
+    for (int i = tid; i < n; i += GP_THREADS) {
+      const double y = S.sy[i] / scale, ye = S.sn[i] / scale;
+      S.sy[i] = y; S.sn[i] = ye * ye + GP_TINY;
+      red[0] += y;
+    }
+    block_sum4(S, red);
+    const double mean = red[0] / (double)n;
+    red[0] = red[1] = red[2] = red[3] = 0.0;
+    for (int i = tid; i < n; i += GP_THREADS) { const double d = S.sy[i] - mean; red[0] += d * d; }
+    block_sum4(S, red);
+    const double var = red[0] / (double)n;
+    const int T = (n + TB - 1) / TB;
+    // ---- hyper-parameter search (multiband_gp.py:129-164)
+    const double p0[4] = {mean, log(var / 2.0), log(100.0 * 100.0), log(6000.0 * 6000.0)};
+    Lbfgs4 opt; opt.start(p0);
+    for (;;) {
+      double f, g[4];
+      gp_eval(S, n, T, opt.x, f, g);
+      if (!opt.advance(f, g)) break;
+    }
+    const double* p = opt.x;
+    if (status && tid == 0) { status[o * 4] = opt.nit; status[o * 4 + 1] = opt.nfev; status[o * 4 + 2] = opt.why; }
+    // ---- features (multiband_gp.py:171-188): positions 0, 1, 2 of the parameter vector, read literally
+    const double amp_f = exp(p[0]), ts_f = sqrt(exp(p[1])), ws_f = sqrt(exp(p[2]));
+    if (tid < GP_COLS) row[tid] = qnan();
+    __syncthreads();
+    if (tid == 0) { row[0] = amp_f; row[1] = ts_f; row[2] = ws_f; row[3] = -opt.f; row[4] = ts_f / (ws_f / 1000.0); }
+    double f_fin, g_fin[4];
+    gp_eval(S, n, T, p, f_fin, g_fin);                 // alpha at the optimum (george recomputes on predict)
+    if (f_fin >= 1e25) continue;
+    // peak time: first flux maximum of the r band in FILE order, else over all rows (:331-338)
+    if (warp == 0) {
+      int lo = off[BR], hi = off[BR + 1];
+      if (hi == lo) { lo = 0; hi = ntot; }
+      double best = -pinf(); int brank = 0x7fffffff, bi = -1;
+      for (int i = lo + lane; i < hi; i += 32) {
+        const double f = gf[base + i];
+        if (is_nan(f)) continue;
+        const int rk = grank[base + i];
+        if (f > best || (f == best && rk < brank)) { best = f; brank = rk; bi = i; }
+      }
+      for (int o2 = 16; o2 > 0; o2 >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o2);
+        const int ork = __shfl_xor_sync(0xffffffffu, brank, o2), oi = __shfl_xor_sync(0xffffffffu, bi, o2);
+        if (oi >= 0 && (bi < 0 || ob > best || (ob == best && ork < brank))) { best = ob; brank = ork; bi = oi; }
+      }
+      if (lane == 0) s_pk = bi;
+    }
+    __syncthreads();
+    if (s_pk < 0) continue;
+    const double pt = gt[base + s_pk] - tmin_all;
+    const KernelPars kp = unpack(p);
+    if (warp < 12) {                                   // 12 predictions, one warp each (:236-262)
+      const int ei = warp / 3, j = warp % 3;
+      const double ep = (ei == 0) ? 0.0 : (ei == 1 ? 20.0 : (ei == 2 ? 50.0 : 100.0));
+      const double tq = pt + ep, lq = c_wave[1 + j];
+      double acc = 0.0;
+      for (int i = lane; i < n; i += 32) {
+        const double dt = tq - S.st[i], dl = lq - S.sl[i];
+        const double s = sqrt(3.0 * (dt * dt / kp.m0 + dl * dl / kp.m1));
+        acc += kp.amp * (1.0 + s) * exp(-s) * S.sb[i];
+      }
+      for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
+      if (lane == 0) S.bc[warp] = (acc + kp.mean) * scale;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double col[4][2];
+      for (int ei = 0; ei < 4; ++ei) {
+        const double fg = S.bc[3 * ei], fr = S.bc[3 * ei + 1], fi = S.bc[3 * ei + 2];
+        row[5 + 5 * ei] = fg; row[6 + 5 * ei] = fr; row[7 + 5 * ei] = fi;
+        col[ei][0] = (fg > 0.0 && fr > 0.0) ? -2.5 * log10(fg / fr) : qnan();
+        col[ei][1] = (fr > 0.0 && fi > 0.0) ? -2.5 * log10(fr / fi) : qnan();
+        row[8 + 5 * ei] = col[ei][0]; row[9 + 5 * ei] = col[ei][1];
+      }
+      if (!is_nan(col[0][0]) && !is_nan(col[2][0])) row[25] = (col[2][0] - col[0][0]) / 50.0;     // :265-277
+      if (!is_nan(col[0][0]) && !is_nan(col[3][0])) row[26] = (col[3][0] - col[0][0]) / 100.0;
+    }
+  }
+}
+
+}  // namespace
+
+int run_gp2d(const mlrn_store* s, double* out_dev, int* status_dev, cudaStream_t st) {
+  if (s->n_obj == 0) return MLRN_OK;
+  const int T_need = (s->max_obs + TB - 1) / TB > 1 ? (s->max_obs + TB - 1) / TB : 1;
+  const int T1 = T_need < T_SMEM_MAX ? T_need : T_SMEM_MAX;
+  {
+    const size_t smem = gp_smem_bytes(T1, true);
+    MLRN_CUDA(cudaFuncSetAttribute(k_gp2d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = s->n_obj < s->sm_count ? s->n_obj : s->sm_count;
+    MLRN_CUDA(cudaMemsetAsync(s->ticket + 2, 0, 2 * sizeof(unsigned long long), st));
+    k_gp2d<true><<<grid, GP_THREADS, smem, st>>>(s->seg_off, s->t, s->flux, s->err, s->rank, s->n_obj, T1, 0, T1 * TB,
+                                                 nullptr, s->ticket + 2, out_dev, status_dev);
+    MLRN_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  if (T_need > T_SMEM_MAX) {                            // long objects: tiles in global scratch
+    const size_t smem = gp_smem_bytes(T_need, false);
+    MLRN_CUDA(cudaFuncSetAttribute(k_gp2d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = s->n_obj < s->sm_count ? s->n_obj : s->sm_count;
+    double* scratch = nullptr;
+    const size_t per_cta = (size_t)(n_tiles(T_need) + T_need) * TT * sizeof(double);
+    MLRN_CUDA(cudaMallocAsync(&scratch, per_cta * grid, st));
+    k_gp2d<false><<<grid, GP_THREADS, smem, st>>>(s->seg_off, s->t, s->flux, s->err, s->rank, s->n_obj, T_need,
+                                                  T1 * TB + 1, T_need * TB, scratch, s->ticket + 3, out_dev, status_dev);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(scratch, st);
+    if (e != cudaSuccess) return cuda_fail(e, "k_gp2d<global> launch");
+    count_launch();
+  }
+  return MLRN_OK;
+}
+
+}  // namespace mlrn
