@@ -33,27 +33,33 @@ constexpr int GP_WARPS = GP_THREADS / 32;
 constexpr int TB = 16;                 // tile edge
 constexpr int TT = TB * TB;            // doubles per tile
 constexpr int GP_COLS = 27;
-constexpr int T_SMEM_MAX = 13;         // 91 tiles + V buffer + vectors < 227 KB
+constexpr int T_SMEM_MAX = 12;         // 78 tiles + V buffer + vectors < 227 KB  (N <= 192 in shared memory)
+constexpr int VLD = 18;                // column stride of a V tile (padding against bank conflicts)
+constexpr int VT = TB * VLD;           // doubles per V tile
+constexpr int LTLD = 17;               // row stride of the transposed pivot inverse
 constexpr double GP_TINY = 1.25e-12;   // george's frozen white-noise floor
 constexpr double LOG_2PI = 1.8378770664093453;
+constexpr unsigned FULLMASK = 0xffffffffu;
 
 __device__ __constant__ double c_wave[6] = {3670.0, 4825.0, 6222.0, 7545.0, 8691.0, 9710.0};
 
 __host__ __device__ inline int n_tiles(int T) { return T * (T + 1) / 2; }
 __host__ __device__ inline size_t gp_fixed_doubles(int np) {
-  // vectors t, lam, y, noise, b (np each) + Lc, Li, LiT tiles + w[16] + reduction scratch
-  return 5 * (size_t)np + 3 * TT + TB + GP_WARPS * 4 + 16;
+  // vectors t, lam, y, noise, b (np each) + Lc + 2 x (Li, LiT, w) + reduction scratch + broadcast slots
+  return 5 * (size_t)np + TT + 2 * (TT + TB * LTLD + TB) + GP_WARPS * 4 + 16;
 }
+__host__ __device__ inline size_t gp_tile_doubles(int T) { return (size_t)n_tiles(T) * TT + (size_t)T * VT; }
 __host__ inline size_t gp_smem_bytes(int T, bool tiles_in_smem) {
   size_t d = gp_fixed_doubles(T * TB);
-  if (tiles_in_smem) d += (size_t)(n_tiles(T) + T) * TT;
+  if (tiles_in_smem) d += gp_tile_doubles(T);
   return d * sizeof(double) + 2 * n_tiles(T) + 64;      // + (I, J) byte table of the tiles
 }
 
 struct GpShared {
-  double *tiles, *vbuf;                 // [n_tiles][256], [T][256]
+  double *tiles, *vbuf;                 // [n_tiles][256], [T][VT]
   double *st, *sl, *sy, *sn, *sb;       // [np]
-  double *Lc, *Li, *LiT, *w, *red, *bc; // pivot factor, its inverse (row-major and transposed), scratch
+  double *Lc, *Li[2], *LiT[2], *w[2];   // pivot factor; its inverse row-major / transposed (stride 17); L^-1 b_k
+  double *red, *bc;                     // reduction scratch, broadcast slots
   unsigned char *tI, *tJ;
 };
 
@@ -65,74 +71,82 @@ __device__ void block_sum4(const GpShared& S, double* v) {
 #pragma unroll
   for (int q = 0; q < 4; ++q)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+    for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(FULLMASK, v[q], o);
   __syncthreads();
   if (lane == 0) for (int q = 0; q < 4; ++q) S.red[warp * 4 + q] = v[q];
   __syncthreads();
   for (int q = 0; q < 4; ++q) { double s = 0.0; for (int w = 0; w < GP_WARPS; ++w) s += S.red[w * 4 + q]; v[q] = s; }
 }
 
-struct KernelPars { double mean, amp, m0, m1; };
+struct KernelPars { double mean, amp, im0, im1; };
 __device__ __forceinline__ KernelPars unpack(const double* p) {
-  KernelPars k; k.mean = p[0]; k.amp = 2.0 * exp(p[1]); k.m0 = exp(p[2]); k.m1 = exp(p[3]); return k;   // ndim * exp(log_constant)
+  KernelPars k; k.mean = p[0]; k.amp = 2.0 * exp(p[1]); k.im0 = exp(-p[2]); k.im1 = exp(-p[3]); return k;   // amp = ndim * exp(log_constant)
 }
 
-// pivot tile: Cholesky, inverse, w = L^-1 b_k.  Executed by warp 0; lanes 0..15 own one row each.
-__device__ void pivot_warp(const GpShared& S, int k, double* quad, double* logdet, int* fail) {
-  const int lane = threadIdx.x & 31;
+// Pivot tile k: L = chol(A_kk) held one row per lane in registers (columns broadcast by shuffle), then
+// L^-1 (one column per lane), w = L^-1 b_k.  One warp.  Results in S.Li/LiT/w[buf]; ln|K| via the product of pivots.
+__device__ void pivot_warp(const GpShared& S, int k, int buf, double& quad, double& logdet, int& fail) {
+  const int lane = threadIdx.x & 31, r = lane & 15;
   const double* A = tile_ptr(S, k, k);
-  double* L = S.Lc;                    // row-major L[r*16 + c]
-  for (int e = lane; e < TT; e += 32) { int r = e & 15, c = e >> 4; L[r * TB + c] = A[c * TB + r]; }
-  __syncwarp();
-  double ld = 0.0; bool bad = false;
+  double row[TB], rinv[TB];
+#pragma unroll
+  for (int c = 0; c < TB; ++c) row[c] = A[c * TB + r];
+  double prod = 1.0; bool bad = false;
+#pragma unroll
   for (int c = 0; c < TB; ++c) {
-    const double piv = L[c * TB + c];
-    if (!(piv > 0.0)) bad = true;
-    const double d = sqrt(piv);
-    ld += log(piv);                    // 2 ln L_cc
-    __syncwarp();
-    if (lane < TB && lane >= c) L[lane * TB + c] = (lane == c) ? d : L[lane * TB + c] / d;
-    __syncwarp();
-    if (lane < TB && lane > c) {
-      const double lrc = L[lane * TB + c];
-      for (int c2 = c + 1; c2 <= lane; ++c2) L[lane * TB + c2] -= lrc * L[c2 * TB + c];
-    }
-    __syncwarp();
+    const double piv = __shfl_sync(FULLMASK, row[c], c);
+    bad = bad || !(piv > 0.0);
+    const double ri = rsqrt(piv);
+    rinv[c] = ri; prod *= piv;
+    const double l = (r == c) ? piv * ri : row[c] * ri;
+    row[c] = l;
+#pragma unroll
+    for (int c2 = c + 1; c2 < TB; ++c2) row[c2] -= l * __shfl_sync(FULLMASK, l, c2);
   }
-  // inverse: lane c (< 16) solves column c of L X = I
   if (lane < TB) {
-    const int c = lane;
-    double x[TB];
 #pragma unroll
-    for (int r = 0; r < TB; ++r) {
-      double s = (r == c) ? 1.0 : 0.0;
+    for (int c = 0; c < TB; ++c) S.Lc[c * TB + r] = row[c];          // L[r][c] at c*16 + r
+  }
+  __syncwarp();
+  {
+    const int j = r;                       // this lane's column of L^-1
+    double acc[TB], x[TB];
 #pragma unroll
-      for (int m = 0; m < TB; ++m) if (m < r) s -= L[r * TB + m] * ((m >= c) ? x[m] : 0.0);
-      x[r] = (r >= c) ? s / L[r * TB + r] : 0.0;
+    for (int q = 0; q < TB; ++q) acc[q] = (q == j) ? 1.0 : 0.0;
+#pragma unroll
+    for (int m = 0; m < TB; ++m) {
+      x[m] = (m >= j) ? acc[m] * rinv[m] : 0.0;
+#pragma unroll
+      for (int q = m + 1; q < TB; ++q) acc[q] -= S.Lc[m * TB + q] * x[m];
     }
+    if (lane < TB) {
 #pragma unroll
-    for (int r = 0; r < TB; ++r) { S.Li[r * TB + c] = x[r]; S.LiT[c * TB + r] = x[r]; }
+      for (int q = 0; q < TB; ++q) { S.Li[buf][q * TB + j] = x[q]; S.LiT[buf][j * LTLD + q] = x[q]; }
+    }
   }
   __syncwarp();
   double wq = 0.0;
   if (lane < TB) {
     double s = 0.0;
-    for (int c = 0; c <= lane; ++c) s += S.Li[lane * TB + c] * S.sb[k * TB + c];
-    S.w[lane] = s; wq = s * s;
+    for (int c = 0; c <= r; ++c) s += S.LiT[buf][c * LTLD + r] * S.sb[k * TB + c];
+    S.w[buf][r] = s; wq = s * s;
   }
-  for (int o = 16; o > 0; o >>= 1) wq += __shfl_xor_sync(0xffffffffu, wq, o);
-  if (lane == 0) { *quad += wq; *logdet += ld; if (bad || !(ld == ld)) *fail = 1; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) wq += __shfl_xor_sync(FULLMASK, wq, o);
+  quad += wq; logdet += log(prod);
+  if (bad || !(prod == prod)) fail = 1;
+  __syncwarp();
 }
 
-// C(16x16, column-major) -= Vi Vj^T, one warp; lane (g = lane/4, h = lane%4) owns rows 2g..2g+1, cols 4h..4h+3
+// C(16x16, column-major) -= Vi Vj^T, one warp; lane (g = lane % 8, h = lane / 8) owns rows 2g..2g+1, cols 4h..4h+3
 __device__ __forceinline__ void tile_update(double* __restrict__ C, const double* __restrict__ Vi, const double* __restrict__ Vj) {
-  const int lane = threadIdx.x & 31, g = lane >> 2, h = lane & 3;
+  const int lane = threadIdx.x & 31, g = lane & 7, h = lane >> 3;
   double acc[2][4] = {};
 #pragma unroll
   for (int m = 0; m < TB; ++m) {
-    const double2 a = *reinterpret_cast<const double2*>(Vi + m * TB + 2 * g);
-    const double2 b0 = *reinterpret_cast<const double2*>(Vj + m * TB + 4 * h);
-    const double2 b1 = *reinterpret_cast<const double2*>(Vj + m * TB + 4 * h + 2);
+    const double2 a = *reinterpret_cast<const double2*>(Vi + m * VLD + 2 * g);
+    const double2 b0 = *reinterpret_cast<const double2*>(Vj + m * VLD + 4 * h);
+    const double2 b1 = *reinterpret_cast<const double2*>(Vj + m * VLD + 4 * h + 2);
     acc[0][0] += a.x * b0.x; acc[0][1] += a.x * b0.y; acc[0][2] += a.x * b1.x; acc[0][3] += a.x * b1.y;
     acc[1][0] += a.y * b0.x; acc[1][1] += a.y * b0.y; acc[1][2] += a.y * b1.x; acc[1][3] += a.y * b1.y;
   }
@@ -147,7 +161,7 @@ __device__ __forceinline__ void tile_update(double* __restrict__ C, const double
 
 // -ln L and its gradient at p.  Leaves alpha in S.sb[0..n).  Result broadcast to every thread.
 __device__ void gp_eval(const GpShared& S, int n, int T, const double* p, double& f, double* grad) {
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const KernelPars kp = unpack(p);
   const int nt = n_tiles(T);
   // ---- (a) kernel matrix, b = y - mean
@@ -158,19 +172,22 @@ __device__ void gp_eval(const GpShared& S, int n, int T, const double* p, double
     if (gi >= n || gj >= n) v = (gi == gj) ? 1.0 : 0.0;
     else {
       const double dt = S.st[gi] - S.st[gj], dl = S.sl[gi] - S.sl[gj];
-      const double s = sqrt(3.0 * (dt * dt / kp.m0 + dl * dl / kp.m1));
+      const double s = sqrt(3.0 * (dt * dt * kp.im0 + dl * dl * kp.im1));
       v = kp.amp * (1.0 + s) * exp(-s);
       if (gi == gj) v += S.sn[gi];
     }
     S.tiles[e] = v;
   }
   for (int i = tid; i < T * TB; i += GP_THREADS) S.sb[i] = (i < n) ? S.sy[i] - kp.mean : 0.0;
-  double quad = 0.0, logdet = 0.0; int fail = 0;      // meaningful in warp 0 / lane 0 only
+  double quad = 0.0, logdet = 0.0; int fail = 0;      // accumulated by warp 0 (uniform across its lanes)
   __syncthreads();
-  // ---- (b) tile sweep
+  // ---- (b) tile sweep with look-ahead: warp 0 owns the critical path (next pivot tile), warps 1.. the bulk
+  if (warp == 0) pivot_warp(S, 0, 0, quad, logdet, fail);
+  __syncthreads();
   for (int k = 0; k < T; ++k) {
-    if (warp == 0) pivot_warp(S, k, &quad, &logdet, &fail);
-    __syncthreads();
+    const int cur = k & 1, nxt = cur ^ 1;
+    const double* Li = S.Li[cur];
+    const double* LiT = S.LiT[cur];
     // V_i = X_i Li^T for i != k
     for (int e = tid; e < (T - 1) * TT; e += GP_THREADS) {
       int i = e >> 8; if (i >= k) ++i;
@@ -179,63 +196,77 @@ __device__ void gp_eval(const GpShared& S, int n, int T, const double* p, double
       if (i > k) {
         const int r = q & 15, c = q >> 4;
         const double* X = tile_ptr(S, i, k);
-        for (int m = 0; m <= c; ++m) s += X[m * TB + r] * S.Li[c * TB + m];
-        S.vbuf[i * TT + c * TB + r] = s;
+        for (int m = 0; m <= c; ++m) s += X[m * TB + r] * Li[c * TB + m];
+        S.vbuf[i * VT + c * VLD + r] = s;
       } else {
         const int c = q & 15, r = q >> 4;
         const double* X = tile_ptr(S, k, i);          // X_i = tile(k, i)^T
-        for (int m = 0; m <= c; ++m) s += X[r * TB + m] * S.LiT[m * TB + c];
-        S.vbuf[i * TT + c * TB + r] = s;
+        for (int m = 0; m <= c; ++m) s += X[r * TB + m] * LiT[m * LTLD + c];
+        S.vbuf[i * VT + c * VLD + r] = s;
       }
     }
     __syncthreads();
-    // rank-16 updates of every tile outside row/column k (warp per tile)
-    {
+    if (warp == 0) {
+      if (k + 1 < T) {                                // finish row k+1 of this step first, then factor it
+        const double* V = S.vbuf + (k + 1) * VT;
+        tile_update(tile_ptr(S, k + 1, k + 1), V, V);
+        if (lane < TB) {
+          double s = 0.0;
+          for (int m = 0; m < TB; ++m) s += V[m * VLD + lane] * S.w[cur][m];
+          S.sb[(k + 1) * TB + lane] -= s;
+        }
+        __syncwarp();
+        pivot_warp(S, k + 1, nxt, quad, logdet, fail);
+      }
+    } else {
+      // rank-16 updates of every tile outside row/column k (warp per tile); (k+1, k+1) belongs to warp 0
       const int Tm = T - 1, ntask = Tm * (Tm + 1) / 2;
-      for (int task = warp; task < ntask; task += GP_WARPS) {
+      for (int task = warp - 1; task < ntask; task += GP_WARPS - 1) {
         int ii = (int)((sqrt(8.0 * task + 1.0) - 1.0) * 0.5);
         while (ii * (ii + 1) / 2 > task) --ii;
         while ((ii + 1) * (ii + 2) / 2 <= task) ++ii;
-        int jj = task - ii * (ii + 1) / 2;
+        const int jj = task - ii * (ii + 1) / 2;
         const int i = ii + (ii >= k), j = jj + (jj >= k);
-        tile_update(tile_ptr(S, i, j), S.vbuf + i * TT, S.vbuf + j * TT);
+        if (i == k + 1 && j == k + 1) continue;
+        tile_update(tile_ptr(S, i, j), S.vbuf + i * VT, S.vbuf + j * VT);
       }
-    }
-    // column k <- V_i Li (i != k); pivot tile <- -(Li^T Li); b updates.  Disjoint from the updates above.
-    for (int e = tid; e < (T - 1) * TT; e += GP_THREADS) {
-      int i = e >> 8; if (i >= k) ++i;
-      const int q = e & 255;
-      const double* V = S.vbuf + i * TT;
-      double s = 0.0;
-      if (i > k) {
-        const int r = q & 15, c = q >> 4;
-        for (int m = c; m < TB; ++m) s += V[m * TB + r] * S.Li[m * TB + c];
-        tile_ptr(S, i, k)[c * TB + r] = s;
-      } else {
-        const int c = q & 15, r = q >> 4;
-        for (int m = c; m < TB; ++m) s += V[m * TB + r] * S.Li[m * TB + c];
-        tile_ptr(S, k, i)[r * TB + c] = s;            // transposed store
-      }
-    }
-    for (int e = tid; e < TT; e += GP_THREADS) {
-      const int r = e & 15, c = e >> 4;
-      double s = 0.0;
-      for (int m = (r > c ? r : c); m < TB; ++m) s += S.LiT[r * TB + m] * S.LiT[c * TB + m];
-      tile_ptr(S, k, k)[c * TB + r] = -s;
-    }
-    for (int i = tid; i < T * TB; i += GP_THREADS) {
-      const int ti = i >> 4, r = i & 15;
-      if (ti != k) {
-        const double* V = S.vbuf + ti * TT;
+      // column k <- V_i Li (i != k); pivot tile <- -(Li^T Li); b_i -= V_i w.  Disjoint from the updates.
+      const int t2 = tid - 32, nth = GP_THREADS - 32;
+      for (int e = t2; e < (T - 1) * TT; e += nth) {
+        int i = e >> 8; if (i >= k) ++i;
+        const int q = e & 255;
+        const double* V = S.vbuf + i * VT;
         double s = 0.0;
-        for (int m = 0; m < TB; ++m) s += V[m * TB + r] * S.w[m];
-        S.sb[i] -= s;
+        if (i > k) {
+          const int r = q & 15, c = q >> 4;
+          for (int m = c; m < TB; ++m) s += V[m * VLD + r] * Li[m * TB + c];
+          tile_ptr(S, i, k)[c * TB + r] = s;
+        } else {
+          const int c = q & 15, r = q >> 4;
+          for (int m = c; m < TB; ++m) s += V[m * VLD + r] * Li[m * TB + c];
+          tile_ptr(S, k, i)[r * TB + c] = s;          // transposed store
+        }
+      }
+      for (int e = t2; e < TT; e += nth) {
+        const int r = e & 15, c = e >> 4;
+        double s = 0.0;
+        for (int m = (r > c ? r : c); m < TB; ++m) s += Li[m * TB + r] * Li[m * TB + c];
+        tile_ptr(S, k, k)[c * TB + r] = -s;
+      }
+      for (int i = t2; i < T * TB; i += nth) {
+        const int ti = i >> 4, r = i & 15;
+        if (ti != k && ti != k + 1) {
+          const double* V = S.vbuf + ti * VT;
+          double s = 0.0;
+          for (int m = 0; m < TB; ++m) s += V[m * VLD + r] * S.w[cur][m];
+          S.sb[i] -= s;
+        }
       }
     }
     __syncthreads();
     if (tid < TB) {                                   // b_k <- Li^T w  (after every reader of the old b_k / w)
       double s = 0.0;
-      for (int m = tid; m < TB; ++m) s += S.Li[m * TB + tid] * S.w[m];
+      for (int m = tid; m < TB; ++m) s += Li[m * TB + tid] * S.w[cur][m];
       S.sb[k * TB + tid] = s;
     }
   }
@@ -251,7 +282,7 @@ __device__ void gp_eval(const GpShared& S, int n, int T, const double* p, double
       const double wgt = (I == J) ? 1.0 : 2.0;
       const double Aij = wgt * (S.sb[gi] * S.sb[gj] + S.tiles[e]);
       const double dt = S.st[gi] - S.st[gj], dl = S.sl[gi] - S.sl[gj];
-      const double a0 = dt * dt / kp.m0, a1 = dl * dl / kp.m1;
+      const double a0 = dt * dt * kp.im0, a1 = dl * dl * kp.im1;
       const double s = sqrt(3.0 * (a0 + a1)), ex = exp(-s);
       const double dk = 1.5 * kp.amp * ex;
       acc[1] += Aij * kp.amp * (1.0 + s) * ex; acc[2] += Aij * dk * a0; acc[3] += Aij * dk * a1;
@@ -278,15 +309,19 @@ k_gp2d(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
   __shared__ long long s_obj;
   __shared__ int s_cnt[GP_WARPS + 1];
   __shared__ int s_pk;
+  __shared__ int s_go;
+  __shared__ Lbfgs4 s_opt;              // optimiser state: advanced by thread 0, x broadcast to the CTA
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int np_cap = T_cap * TB;
   GpShared S;
   {
     double* d = (double*)smem_raw;
     S.st = d; d += np_cap; S.sl = d; d += np_cap; S.sy = d; d += np_cap; S.sn = d; d += np_cap; S.sb = d; d += np_cap;
-    S.Lc = d; d += TT; S.Li = d; d += TT; S.LiT = d; d += TT; S.w = d; d += TB; S.red = d; d += GP_WARPS * 4; S.bc = d; d += 16;
-    if (SMEM_TILES) { S.tiles = d; d += (size_t)n_tiles(T_cap) * TT; S.vbuf = d; d += (size_t)T_cap * TT; }
-    else { S.tiles = gscratch + (size_t)blockIdx.x * (n_tiles(T_cap) + T_cap) * TT; S.vbuf = S.tiles + (size_t)n_tiles(T_cap) * TT; }
+    S.Lc = d; d += TT;
+    for (int q = 0; q < 2; ++q) { S.Li[q] = d; d += TT; S.LiT[q] = d; d += TB * LTLD; S.w[q] = d; d += TB; }
+    S.red = d; d += GP_WARPS * 4; S.bc = d; d += 16;
+    if (SMEM_TILES) { S.tiles = d; d += (size_t)n_tiles(T_cap) * TT; S.vbuf = d; d += (size_t)T_cap * VT; }
+    else { S.tiles = gscratch + (size_t)blockIdx.x * gp_tile_doubles(T_cap); S.vbuf = S.tiles + (size_t)n_tiles(T_cap) * TT; }
     S.tI = (unsigned char*)d; S.tJ = S.tI + n_tiles(T_cap);
   }
   for (int tl = tid; tl < n_tiles(T_cap); tl += GP_THREADS) {
@@ -380,19 +415,24 @@ k_gp2d(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
     const int T = (n + TB - 1) / TB;
     // ---- hyper-parameter search (multiband_gp.py:129-164)
     const double p0[4] = {mean, log(var / 2.0), log(100.0 * 100.0), log(6000.0 * 6000.0)};
-    Lbfgs4 opt; opt.start(p0);
+    if (tid == 0) s_opt.start(p0);
+    __syncthreads();
     for (;;) {
       double f, g[4];
-      gp_eval(S, n, T, opt.x, f, g);
-      if (!opt.advance(f, g)) break;
+      const double xk[4] = {s_opt.x[0], s_opt.x[1], s_opt.x[2], s_opt.x[3]};
+      gp_eval(S, n, T, xk, f, g);                      // ends with a barrier: everyone has read x
+      if (tid == 0) s_go = s_opt.advance(f, g) ? 1 : 0;
+      __syncthreads();
+      if (!s_go) break;
     }
-    const double* p = opt.x;
-    if (status && tid == 0) { status[o * 4] = opt.nit; status[o * 4 + 1] = opt.nfev; status[o * 4 + 2] = opt.why; }
+    const double p[4] = {s_opt.x[0], s_opt.x[1], s_opt.x[2], s_opt.x[3]};
+    const double f_opt = s_opt.f;
+    if (status && tid == 0) { status[o * 4] = s_opt.nit; status[o * 4 + 1] = s_opt.nfev; status[o * 4 + 2] = s_opt.why; }
     // ---- features (multiband_gp.py:171-188): positions 0, 1, 2 of the parameter vector, read literally
     const double amp_f = exp(p[0]), ts_f = sqrt(exp(p[1])), ws_f = sqrt(exp(p[2]));
     if (tid < GP_COLS) row[tid] = qnan();
     __syncthreads();
-    if (tid == 0) { row[0] = amp_f; row[1] = ts_f; row[2] = ws_f; row[3] = -opt.f; row[4] = ts_f / (ws_f / 1000.0); }
+    if (tid == 0) { row[0] = amp_f; row[1] = ts_f; row[2] = ws_f; row[3] = -f_opt; row[4] = ts_f / (ws_f / 1000.0); }
     double f_fin, g_fin[4];
     gp_eval(S, n, T, p, f_fin, g_fin);                 // alpha at the optimum (george recomputes on predict)
     if (f_fin >= 1e25) continue;
@@ -425,7 +465,7 @@ k_gp2d(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
       double acc = 0.0;
       for (int i = lane; i < n; i += 32) {
         const double dt = tq - S.st[i], dl = lq - S.sl[i];
-        const double s = sqrt(3.0 * (dt * dt / kp.m0 + dl * dl / kp.m1));
+        const double s = sqrt(3.0 * (dt * dt * kp.im0 + dl * dl * kp.im1));
         acc += kp.amp * (1.0 + s) * exp(-s) * S.sb[i];
       }
       for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
@@ -468,7 +508,7 @@ int run_gp2d(const mlrn_store* s, double* out_dev, int* status_dev, cudaStream_t
     MLRN_CUDA(cudaFuncSetAttribute(k_gp2d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = s->n_obj < s->sm_count ? s->n_obj : s->sm_count;
     double* scratch = nullptr;
-    const size_t per_cta = (size_t)(n_tiles(T_need) + T_need) * TT * sizeof(double);
+    const size_t per_cta = gp_tile_doubles(T_need) * sizeof(double);
     MLRN_CUDA(cudaMallocAsync(&scratch, per_cta * grid, st));
     k_gp2d<false><<<grid, GP_THREADS, smem, st>>>(s->seg_off, s->t, s->flux, s->err, s->rank, s->n_obj, T_need,
                                                   T1 * TB + 1, T_need * TB, scratch, s->ticket + 3, out_dev, status_dev);

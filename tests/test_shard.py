@@ -1,0 +1,76 @@
+"""Host-side sharding logic and the all-gather plumbing (world_size 2, gloo, CPU)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+
+def test_balanced_ranges_cover_everything_once():
+    from mallorn_astrophysics_b200.shard import balanced_ranges
+    rng = np.random.default_rng(0)
+    for n, world in ((0, 4), (1, 4), (3, 8), (1000, 1), (1000, 2), (1000, 8), (10178, 8)):
+        w = rng.integers(30, 400, size=n).astype(float)
+        ranges = balanced_ranges(w, world)
+        assert len(ranges) == world and ranges[0][0] == 0 and ranges[-1][1] == n
+        assert all(a <= b for a, b in ranges) and all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+        if n >= 100 * world:
+            sums = np.array([w[a:b].sum() for a, b in ranges])
+            assert sums.max() - sums.min() <= 2 * w.max()          # within one object of perfect balance per cut
+
+
+def test_cubic_cost_balances_the_gp_pass():
+    from mallorn_astrophysics_b200.shard import balanced_ranges, object_costs
+    from mallorn_astrophysics_b200.synth import make_table
+    tb = make_table(2000, config_index=1)
+    c3 = object_costs(tb.obj, tb.n_obj, "cubic")
+    ranges = balanced_ranges(c3, 4)
+    sums = np.array([c3[a:b].sum() for a, b in ranges])
+    assert sums.max() / sums.mean() < 1.02
+    keep_all = np.zeros(tb.n_rows, bool)
+    from mallorn_astrophysics_b200.shard import shard_rows
+    for a, b in ranges:
+        keep, local = shard_rows(tb.obj, a, b)
+        assert not (keep & keep_all).any() and (local >= 0).all() and (local.max(initial=-1) < b - a)
+        keep_all |= keep
+    assert keep_all.all()
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, rows_per_rank, cols, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mallorn_astrophysics_b200.shard import allgather_rows
+    start = sum(rows_per_rank[:rank])
+    local = (torch.arange(rows_per_rank[rank] * cols, dtype=torch.float64).reshape(rows_per_rank[rank], cols)
+             + 1000.0 * start * cols)
+    local[:, 0] = torch.arange(start, start + rows_per_rank[rank], dtype=torch.float64)    # global object index
+    full = allgather_rows(local, rows_per_rank)
+    q.put((rank, full.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("rows_per_rank", [[5, 5], [7, 3], [0, 4]])
+def test_allgather_rows_world2_gloo(rows_per_rank):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, rows_per_rank, 6, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    total = sum(rows_per_rank)
+    for r in range(2):
+        assert got[r].shape == (total, 6)
+        assert np.array_equal(got[r][:, 0], np.arange(total))      # object order preserved, padding stripped
+    assert np.array_equal(got[0], got[1])                           # every rank holds the same table
