@@ -21,7 +21,7 @@ __device__ __forceinline__ long long next_ticket(unsigned long long* counter, in
   return (long long)__shfl_sync(0xffffffffu, v, 0);
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_bazin(const long long* __restrict__ seg_off, const double* __restrict__ gt, const double* __restrict__ gf,
         const double* __restrict__ ge, int n_obj, int cap, unsigned long long* __restrict__ ticket,
         double* __restrict__ out, int* __restrict__ status) {
@@ -51,7 +51,7 @@ k_bazin(const long long* __restrict__ seg_off, const double* __restrict__ gt, co
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_powerlaw(const long long* __restrict__ seg_off, const double* __restrict__ gt, const double* __restrict__ gf,
            int n_obj, int cap, unsigned long long* __restrict__ ticket, double* __restrict__ out,
            int* __restrict__ status) {
@@ -117,8 +117,8 @@ int run_powerlaw(const mlrn_store* s, double* out_dev, int* status_dev, cudaStre
   int warps, grid; size_t smem;
   int rc = fit_geometry(k_powerlaw, decline_warp_doubles(cap) * sizeof(double), s, warps, smem, grid);
   if (rc != MLRN_OK) return rc;
-  MLRN_CUDA(cudaMemsetAsync(s->ticket, 0, sizeof(unsigned long long), st));
-  k_powerlaw<<<grid, warps * 32, smem, st>>>(s->seg_off, s->t, s->flux, s->n_obj, cap, s->ticket, out_dev, status_dev);
+  MLRN_CUDA(cudaMemsetAsync(s->ticket + 1, 0, sizeof(unsigned long long), st));
+  k_powerlaw<<<grid, warps * 32, smem, st>>>(s->seg_off, s->t, s->flux, s->n_obj, cap, s->ticket + 1, out_dev, status_dev);
   MLRN_CUDA(cudaGetLastError());
   count_launch();
   return MLRN_OK;

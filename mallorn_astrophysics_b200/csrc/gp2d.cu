@@ -36,7 +36,6 @@ constexpr int GP_COLS = 27;
 constexpr int T_SMEM_MAX = 12;         // 78 tiles + V buffer + vectors < 227 KB  (N <= 192 in shared memory)
 constexpr int VLD = 18;                // column stride of a V tile (padding against bank conflicts)
 constexpr int VT = TB * VLD;           // doubles per V tile
-constexpr int LTLD = 17;               // row stride of the transposed pivot inverse
 constexpr double GP_TINY = 1.25e-12;   // george's frozen white-noise floor
 constexpr double LOG_2PI = 1.8378770664093453;
 constexpr unsigned FULLMASK = 0xffffffffu;
@@ -46,7 +45,7 @@ __device__ __constant__ double c_wave[6] = {3670.0, 4825.0, 6222.0, 7545.0, 8691
 __host__ __device__ inline int n_tiles(int T) { return T * (T + 1) / 2; }
 __host__ __device__ inline size_t gp_fixed_doubles(int np) {
   // vectors t, lam, y, noise, b (np each) + Lc + 2 x (Li, LiT, w) + reduction scratch + broadcast slots
-  return 5 * (size_t)np + TT + 2 * (TT + TB * LTLD + TB) + GP_WARPS * 4 + 16;
+  return 5 * (size_t)np + TT + 2 * (TT + VT + TB) + GP_WARPS * 4 + 16;
 }
 __host__ __device__ inline size_t gp_tile_doubles(int T) { return (size_t)n_tiles(T) * TT + (size_t)T * VT; }
 __host__ inline size_t gp_smem_bytes(int T, bool tiles_in_smem) {
@@ -58,7 +57,7 @@ __host__ inline size_t gp_smem_bytes(int T, bool tiles_in_smem) {
 struct GpShared {
   double *tiles, *vbuf;                 // [n_tiles][256], [T][VT]
   double *st, *sl, *sy, *sn, *sb;       // [np]
-  double *Lc, *Li[2], *LiT[2], *w[2];   // pivot factor; its inverse row-major / transposed (stride 17); L^-1 b_k
+  double *Lc, *Li, *LiT, *w;              // pivot factor; its inverse row-major / transposed (stride VLD); L^-1 b_k
   double *red, *bc;                     // reduction scratch, broadcast slots
   unsigned char *tI, *tJ;
 };
@@ -83,14 +82,19 @@ __device__ __forceinline__ KernelPars unpack(const double* p) {
   KernelPars k; k.mean = p[0]; k.amp = 2.0 * exp(p[1]); k.im0 = exp(-p[2]); k.im1 = exp(-p[3]); return k;   // amp = ndim * exp(log_constant)
 }
 
+// tile element (r, c): column-major with the row index XOR-swizzled by an even number, so that both a
+// column of the tile (r varies) and a row of it (c varies: the transposed reads of the sweep) spread
+// over the shared-memory banks, and (r, r+1) pairs with r even stay one aligned double2
+__device__ __forceinline__ int tix(int r, int c) { return c * TB + (r ^ (c & 14)); }
+
 // Pivot tile k: L = chol(A_kk) held one row per lane in registers (columns broadcast by shuffle), then
 // L^-1 (one column per lane), w = L^-1 b_k.  One warp.  Results in S.Li/LiT/w[buf]; ln|K| via the product of pivots.
-__device__ void pivot_warp(const GpShared& S, int k, int buf, double& quad, double& logdet, int& fail) {
+__device__ __forceinline__ void pivot_warp(const GpShared& S, int k, int buf, double& quad, double& logdet, int& fail) {
   const int lane = threadIdx.x & 31, r = lane & 15;
   const double* A = tile_ptr(S, k, k);
   double row[TB], rinv[TB];
 #pragma unroll
-  for (int c = 0; c < TB; ++c) row[c] = A[c * TB + r];
+  for (int c = 0; c < TB; ++c) row[c] = A[tix(r, c)];
   double prod = 1.0; bool bad = false;
 #pragma unroll
   for (int c = 0; c < TB; ++c) {
@@ -121,15 +125,15 @@ __device__ void pivot_warp(const GpShared& S, int k, int buf, double& quad, doub
     }
     if (lane < TB) {
 #pragma unroll
-      for (int q = 0; q < TB; ++q) { S.Li[buf][q * TB + j] = x[q]; S.LiT[buf][j * LTLD + q] = x[q]; }
+      for (int q = 0; q < TB; ++q) { S.Li[buf * TT + q * TB + j] = x[q]; S.LiT[buf * VT + j * VLD + q] = x[q]; }   // Li[q][j]
     }
   }
   __syncwarp();
   double wq = 0.0;
   if (lane < TB) {
     double s = 0.0;
-    for (int c = 0; c <= r; ++c) s += S.LiT[buf][c * LTLD + r] * S.sb[k * TB + c];
-    S.w[buf][r] = s; wq = s * s;
+    for (int c = 0; c <= r; ++c) s += S.Li[buf * TT + r * TB + c] * S.sb[k * TB + c];
+    S.w[buf * TB + r] = s; wq = s * s;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) wq += __shfl_xor_sync(FULLMASK, wq, o);
@@ -138,7 +142,12 @@ __device__ void pivot_warp(const GpShared& S, int k, int buf, double& quad, doub
   __syncwarp();
 }
 
-// C(16x16, column-major) -= Vi Vj^T, one warp; lane (g = lane % 8, h = lane / 8) owns rows 2g..2g+1, cols 4h..4h+3
+// ---- warp-level 16x16x16 FP64 products; lane (g = lane % 8, h = lane / 8) owns rows 2g..2g+1, cols 4h..4h+3
+#define MLRN_FMA8(acc, a, b0, b1)                                                                     \
+  acc[0][0] += a.x * b0.x; acc[0][1] += a.x * b0.y; acc[0][2] += a.x * b1.x; acc[0][3] += a.x * b1.y;  \
+  acc[1][0] += a.y * b0.x; acc[1][1] += a.y * b0.y; acc[1][2] += a.y * b1.x; acc[1][3] += a.y * b1.y;
+
+// C(i, j) -= Vi Vj^T
 __device__ __forceinline__ void tile_update(double* __restrict__ C, const double* __restrict__ Vi, const double* __restrict__ Vj) {
   const int lane = threadIdx.x & 31, g = lane & 7, h = lane >> 3;
   double acc[2][4] = {};
@@ -147,23 +156,85 @@ __device__ __forceinline__ void tile_update(double* __restrict__ C, const double
     const double2 a = *reinterpret_cast<const double2*>(Vi + m * VLD + 2 * g);
     const double2 b0 = *reinterpret_cast<const double2*>(Vj + m * VLD + 4 * h);
     const double2 b1 = *reinterpret_cast<const double2*>(Vj + m * VLD + 4 * h + 2);
-    acc[0][0] += a.x * b0.x; acc[0][1] += a.x * b0.y; acc[0][2] += a.x * b1.x; acc[0][3] += a.x * b1.y;
-    acc[1][0] += a.y * b0.x; acc[1][1] += a.y * b0.y; acc[1][2] += a.y * b1.x; acc[1][3] += a.y * b1.y;
+    MLRN_FMA8(acc, a, b0, b1)
   }
 #pragma unroll
   for (int cc = 0; cc < 4; ++cc) {
-    double2* p = reinterpret_cast<double2*>(C + (4 * h + cc) * TB + 2 * g);
+    const int c = 4 * h + cc;
+    double2* p = reinterpret_cast<double2*>(C + c * TB + ((2 * g) ^ (c & 14)));
     double2 v = *p;
     v.x -= acc[0][cc]; v.y -= acc[1][cc];
     *p = v;
   }
 }
 
+// V = X Li^T, X = block (i, k) of the symmetric matrix: tile(i, k) if i > k, tile(k, i)^T if i < k
+__device__ __forceinline__ void tile_scale(double* __restrict__ V, const double* __restrict__ X, bool transposed,
+                                           const double* __restrict__ LiT) {
+  const int lane = threadIdx.x & 31, g = lane & 7, h = lane >> 3;
+  double acc[2][4] = {};
+  if (!transposed) {
+#pragma unroll
+    for (int m = 0; m < TB; ++m) {
+      const double2 a = *reinterpret_cast<const double2*>(X + m * TB + ((2 * g) ^ (m & 14)));
+      const double2 b0 = *reinterpret_cast<const double2*>(LiT + m * VLD + 4 * h);
+      const double2 b1 = *reinterpret_cast<const double2*>(LiT + m * VLD + 4 * h + 2);
+      MLRN_FMA8(acc, a, b0, b1)
+    }
+  } else {
+#pragma unroll
+    for (int m = 0; m < TB; ++m) {
+      double2 a;
+      a.x = X[(2 * g) * TB + (m ^ (2 * g))];            // element (m, 2g) of the stored tile
+      a.y = X[(2 * g + 1) * TB + (m ^ (2 * g))];
+      const double2 b0 = *reinterpret_cast<const double2*>(LiT + m * VLD + 4 * h);
+      const double2 b1 = *reinterpret_cast<const double2*>(LiT + m * VLD + 4 * h + 2);
+      MLRN_FMA8(acc, a, b0, b1)
+    }
+  }
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc)
+    *reinterpret_cast<double2*>(V + (4 * h + cc) * VLD + 2 * g) = make_double2(acc[0][cc], acc[1][cc]);
+}
+
+// block (i, k) <- V Li, written to tile(i, k) or transposed into tile(k, i)
+__device__ __forceinline__ void tile_finalise(double* __restrict__ Tl, bool transposed, const double* __restrict__ V,
+                                              const double* __restrict__ Li) {
+  const int lane = threadIdx.x & 31, g = lane & 7, h = lane >> 3;
+  double acc[2][4] = {};
+#pragma unroll
+  for (int m = 0; m < TB; ++m) {
+    const double2 a = *reinterpret_cast<const double2*>(V + m * VLD + 2 * g);
+    const double2 b0 = *reinterpret_cast<const double2*>(Li + m * TB + 4 * h);
+    const double2 b1 = *reinterpret_cast<const double2*>(Li + m * TB + 4 * h + 2);
+    MLRN_FMA8(acc, a, b0, b1)
+  }
+  if (!transposed) {
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int c = 4 * h + cc;
+      *reinterpret_cast<double2*>(Tl + c * TB + ((2 * g) ^ (c & 14))) = make_double2(acc[0][cc], acc[1][cc]);
+    }
+  } else {
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {                    // stored element (row c, col r) for r = 2g + rr
+      double* base = Tl + (2 * g + rr) * TB;
+      *reinterpret_cast<double2*>(base + ((4 * h) ^ (2 * g))) = make_double2(acc[rr][0], acc[rr][1]);
+      *reinterpret_cast<double2*>(base + ((4 * h + 2) ^ (2 * g))) = make_double2(acc[rr][2], acc[rr][3]);
+    }
+  }
+}
+
 // -ln L and its gradient at p.  Leaves alpha in S.sb[0..n).  Result broadcast to every thread.
-__device__ void gp_eval(const GpShared& S, int n, int T, const double* p, double& f, double* grad) {
+// cache: per-CTA global (L2-resident) scratch [2][nt * 256] holding s and exp(-s) of every matrix element
+// between the build and the gradient contraction.
+__device__ __forceinline__ void gp_eval(const GpShared& S, double* __restrict__ cache, int n, int T, int T_cap,
+                                        const double* p, double& f, double* grad) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const KernelPars kp = unpack(p);
   const int nt = n_tiles(T);
+  double* cache_s = cache;
+  double* cache_e = cache + (size_t)n_tiles(T_cap) * TT;
   // ---- (a) kernel matrix, b = y - mean
   for (int e = tid; e < nt * TT; e += GP_THREADS) {
     const int tl = e >> 8, r = e & 15, c = (e >> 4) & 15;
@@ -173,10 +244,12 @@ __device__ void gp_eval(const GpShared& S, int n, int T, const double* p, double
     else {
       const double dt = S.st[gi] - S.st[gj], dl = S.sl[gi] - S.sl[gj];
       const double s = sqrt(3.0 * (dt * dt * kp.im0 + dl * dl * kp.im1));
-      v = kp.amp * (1.0 + s) * exp(-s);
+      const double ex = exp(-s);
+      cache_s[e] = s; cache_e[e] = ex;
+      v = kp.amp * (1.0 + s) * ex;
       if (gi == gj) v += S.sn[gi];
     }
-    S.tiles[e] = v;
+    S.tiles[tl * TT + tix(r, c)] = v;
   }
   for (int i = tid; i < T * TB; i += GP_THREADS) S.sb[i] = (i < n) ? S.sy[i] - kp.mean : 0.0;
   double quad = 0.0, logdet = 0.0; int fail = 0;      // accumulated by warp 0 (uniform across its lanes)
@@ -186,24 +259,14 @@ __device__ void gp_eval(const GpShared& S, int n, int T, const double* p, double
   __syncthreads();
   for (int k = 0; k < T; ++k) {
     const int cur = k & 1, nxt = cur ^ 1;
-    const double* Li = S.Li[cur];
-    const double* LiT = S.LiT[cur];
-    // V_i = X_i Li^T for i != k
-    for (int e = tid; e < (T - 1) * TT; e += GP_THREADS) {
-      int i = e >> 8; if (i >= k) ++i;
-      const int q = e & 255;
-      double s = 0.0;
-      if (i > k) {
-        const int r = q & 15, c = q >> 4;
-        const double* X = tile_ptr(S, i, k);
-        for (int m = 0; m <= c; ++m) s += X[m * TB + r] * Li[c * TB + m];
-        S.vbuf[i * VT + c * VLD + r] = s;
-      } else {
-        const int c = q & 15, r = q >> 4;
-        const double* X = tile_ptr(S, k, i);          // X_i = tile(k, i)^T
-        for (int m = 0; m <= c; ++m) s += X[r * TB + m] * LiT[m * LTLD + c];
-        S.vbuf[i * VT + c * VLD + r] = s;
-      }
+    const double* Li = S.Li + cur * TT;
+    const double* LiT = S.LiT + cur * VT;
+    const double* wv = S.w + cur * TB;
+    // V_i = X_i Li^T for i != k: one warp per tile row
+    for (int q = warp; q < T - 1; q += GP_WARPS) {
+      const int i = q + (q >= k);
+      if (i > k) tile_scale(S.vbuf + i * VT, tile_ptr(S, i, k), false, LiT);
+      else tile_scale(S.vbuf + i * VT, tile_ptr(S, k, i), true, LiT);
     }
     __syncthreads();
     if (warp == 0) {
@@ -212,53 +275,45 @@ __device__ void gp_eval(const GpShared& S, int n, int T, const double* p, double
         tile_update(tile_ptr(S, k + 1, k + 1), V, V);
         if (lane < TB) {
           double s = 0.0;
-          for (int m = 0; m < TB; ++m) s += V[m * VLD + lane] * S.w[cur][m];
+          for (int m = 0; m < TB; ++m) s += V[m * VLD + lane] * wv[m];
           S.sb[(k + 1) * TB + lane] -= s;
         }
         __syncwarp();
         pivot_warp(S, k + 1, nxt, quad, logdet, fail);
       }
     } else {
-      // rank-16 updates of every tile outside row/column k (warp per tile); (k+1, k+1) belongs to warp 0
-      const int Tm = T - 1, ntask = Tm * (Tm + 1) / 2;
-      for (int task = warp - 1; task < ntask; task += GP_WARPS - 1) {
-        int ii = (int)((sqrt(8.0 * task + 1.0) - 1.0) * 0.5);
-        while (ii * (ii + 1) / 2 > task) --ii;
-        while ((ii + 1) * (ii + 2) / 2 <= task) ++ii;
-        const int jj = task - ii * (ii + 1) / 2;
-        const int i = ii + (ii >= k), j = jj + (jj >= k);
-        if (i == k + 1 && j == k + 1) continue;
-        tile_update(tile_ptr(S, i, j), S.vbuf + i * VT, S.vbuf + j * VT);
-      }
-      // column k <- V_i Li (i != k); pivot tile <- -(Li^T Li); b_i -= V_i w.  Disjoint from the updates.
-      const int t2 = tid - 32, nth = GP_THREADS - 32;
-      for (int e = t2; e < (T - 1) * TT; e += nth) {
-        int i = e >> 8; if (i >= k) ++i;
-        const int q = e & 255;
-        const double* V = S.vbuf + i * VT;
-        double s = 0.0;
-        if (i > k) {
-          const int r = q & 15, c = q >> 4;
-          for (int m = c; m < TB; ++m) s += V[m * VLD + r] * Li[m * TB + c];
-          tile_ptr(S, i, k)[c * TB + r] = s;
+      // warp tasks: rank-16 updates of every tile outside row/column k ((k+1, k+1) belongs to warp 0),
+      // then column k <- V_i Li.  Disjoint tiles, so no ordering between them.
+      const int Tm = T - 1, nupd = Tm * (Tm + 1) / 2;
+      for (int task = warp - 1; task < nupd + Tm; task += GP_WARPS - 1) {
+        if (task < nupd) {
+          int ii = (int)((sqrt(8.0 * task + 1.0) - 1.0) * 0.5);
+          while (ii * (ii + 1) / 2 > task) --ii;
+          while ((ii + 1) * (ii + 2) / 2 <= task) ++ii;
+          const int jj = task - ii * (ii + 1) / 2;
+          const int i = ii + (ii >= k), j = jj + (jj >= k);
+          if (i == k + 1 && j == k + 1) continue;
+          tile_update(tile_ptr(S, i, j), S.vbuf + i * VT, S.vbuf + j * VT);
         } else {
-          const int c = q & 15, r = q >> 4;
-          for (int m = c; m < TB; ++m) s += V[m * VLD + r] * Li[m * TB + c];
-          tile_ptr(S, k, i)[r * TB + c] = s;          // transposed store
+          const int q = task - nupd, i = q + (q >= k);
+          if (i > k) tile_finalise(tile_ptr(S, i, k), false, S.vbuf + i * VT, Li);
+          else tile_finalise(tile_ptr(S, k, i), true, S.vbuf + i * VT, Li);
         }
       }
+      // pivot tile <- -(Li^T Li); b_i -= V_i w
+      const int t2 = tid - 32, nth = GP_THREADS - 32;
       for (int e = t2; e < TT; e += nth) {
         const int r = e & 15, c = e >> 4;
         double s = 0.0;
         for (int m = (r > c ? r : c); m < TB; ++m) s += Li[m * TB + r] * Li[m * TB + c];
-        tile_ptr(S, k, k)[c * TB + r] = -s;
+        tile_ptr(S, k, k)[tix(r, c)] = -s;
       }
       for (int i = t2; i < T * TB; i += nth) {
         const int ti = i >> 4, r = i & 15;
         if (ti != k && ti != k + 1) {
           const double* V = S.vbuf + ti * VT;
           double s = 0.0;
-          for (int m = 0; m < TB; ++m) s += V[m * VLD + r] * S.w[cur][m];
+          for (int m = 0; m < TB; ++m) s += V[m * VLD + r] * wv[m];
           S.sb[i] -= s;
         }
       }
@@ -266,7 +321,7 @@ __device__ void gp_eval(const GpShared& S, int n, int T, const double* p, double
     __syncthreads();
     if (tid < TB) {                                   // b_k <- Li^T w  (after every reader of the old b_k / w)
       double s = 0.0;
-      for (int m = tid; m < TB; ++m) s += Li[m * TB + tid] * S.w[cur][m];
+      for (int m = tid; m < TB; ++m) s += Li[m * TB + tid] * wv[m];
       S.sb[k * TB + tid] = s;
     }
   }
@@ -280,10 +335,10 @@ __device__ void gp_eval(const GpShared& S, int n, int T, const double* p, double
     const int gi = I * TB + r, gj = J * TB + c;
     if (gi < n && gj < n) {
       const double wgt = (I == J) ? 1.0 : 2.0;
-      const double Aij = wgt * (S.sb[gi] * S.sb[gj] + S.tiles[e]);
+      const double Aij = wgt * (S.sb[gi] * S.sb[gj] + S.tiles[tl * TT + tix(r, c)]);
       const double dt = S.st[gi] - S.st[gj], dl = S.sl[gi] - S.sl[gj];
       const double a0 = dt * dt * kp.im0, a1 = dl * dl * kp.im1;
-      const double s = sqrt(3.0 * (a0 + a1)), ex = exp(-s);
+      const double s = cache_s[e], ex = cache_e[e];
       const double dk = 1.5 * kp.amp * ex;
       acc[1] += Aij * kp.amp * (1.0 + s) * ex; acc[2] += Aij * dk * a0; acc[3] += Aij * dk * a1;
     }
@@ -303,7 +358,7 @@ template <bool SMEM_TILES>
 __global__ void __launch_bounds__(GP_THREADS, 1)
 k_gp2d(const long long* __restrict__ seg_off, const double* __restrict__ gt, const double* __restrict__ gf,
        const double* __restrict__ ge, const unsigned short* __restrict__ grank, int n_obj, int T_cap, int n_lo,
-       int n_hi, double* __restrict__ gscratch, unsigned long long* __restrict__ ticket, double* __restrict__ out,
+       int n_hi, double* __restrict__ gscratch, double* __restrict__ gcache, unsigned long long* __restrict__ ticket, double* __restrict__ out,
        int* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ long long s_obj;
@@ -318,11 +373,20 @@ k_gp2d(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
     double* d = (double*)smem_raw;
     S.st = d; d += np_cap; S.sl = d; d += np_cap; S.sy = d; d += np_cap; S.sn = d; d += np_cap; S.sb = d; d += np_cap;
     S.Lc = d; d += TT;
-    for (int q = 0; q < 2; ++q) { S.Li[q] = d; d += TT; S.LiT[q] = d; d += TB * LTLD; S.w[q] = d; d += TB; }
+    S.Li = d; d += 2 * TT; S.LiT = d; d += 2 * VT; S.w = d; d += 2 * TB;      // double-buffered (look-ahead)
     S.red = d; d += GP_WARPS * 4; S.bc = d; d += 16;
     if (SMEM_TILES) { S.tiles = d; d += (size_t)n_tiles(T_cap) * TT; S.vbuf = d; d += (size_t)T_cap * VT; }
     else { S.tiles = gscratch + (size_t)blockIdx.x * gp_tile_doubles(T_cap); S.vbuf = S.tiles + (size_t)n_tiles(T_cap) * TT; }
     S.tI = (unsigned char*)d; S.tJ = S.tI + n_tiles(T_cap);
+    // address-space hints: everything carved from the dynamic shared array is shared memory
+    __builtin_assume(__isShared(S.st)); __builtin_assume(__isShared(S.sl)); __builtin_assume(__isShared(S.sy));
+    __builtin_assume(__isShared(S.sn)); __builtin_assume(__isShared(S.sb)); __builtin_assume(__isShared(S.Lc));
+    __builtin_assume(__isShared(S.Li));
+    __builtin_assume(__isShared(S.LiT));
+    __builtin_assume(__isShared(S.w));
+    __builtin_assume(__isShared(S.red)); __builtin_assume(__isShared(S.bc));
+    __builtin_assume(__isShared(S.tI)); __builtin_assume(__isShared(S.tJ));
+    if (SMEM_TILES) { __builtin_assume(__isShared(S.tiles)); __builtin_assume(__isShared(S.vbuf)); }
   }
   for (int tl = tid; tl < n_tiles(T_cap); tl += GP_THREADS) {
     int I = (int)((sqrt(8.0 * tl + 1.0) - 1.0) * 0.5);
@@ -417,13 +481,16 @@ k_gp2d(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
     const double p0[4] = {mean, log(var / 2.0), log(100.0 * 100.0), log(6000.0 * 6000.0)};
     if (tid == 0) s_opt.start(p0);
     __syncthreads();
-    for (;;) {
+    double* cache = gcache + (size_t)blockIdx.x * 2 * n_tiles(T_cap) * TT;
+    double f_fin = 0.0;
+    for (int searching = 1;;) {
       double f, g[4];
       const double xk[4] = {s_opt.x[0], s_opt.x[1], s_opt.x[2], s_opt.x[3]};
-      gp_eval(S, n, T, xk, f, g);                      // ends with a barrier: everyone has read x
+      gp_eval(S, cache, n, T, T_cap, xk, f, g);        // ends with a barrier: everyone has read x
+      if (!searching) { f_fin = f; break; }            // that was the evaluation at the optimum (alpha for predict)
       if (tid == 0) s_go = s_opt.advance(f, g) ? 1 : 0;
       __syncthreads();
-      if (!s_go) break;
+      if (!s_go) searching = 0;
     }
     const double p[4] = {s_opt.x[0], s_opt.x[1], s_opt.x[2], s_opt.x[3]};
     const double f_opt = s_opt.f;
@@ -433,8 +500,6 @@ k_gp2d(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
     if (tid < GP_COLS) row[tid] = qnan();
     __syncthreads();
     if (tid == 0) { row[0] = amp_f; row[1] = ts_f; row[2] = ws_f; row[3] = -f_opt; row[4] = ts_f / (ws_f / 1000.0); }
-    double f_fin, g_fin[4];
-    gp_eval(S, n, T, p, f_fin, g_fin);                 // alpha at the optimum (george recomputes on predict)
     if (f_fin >= 1e25) continue;
     // peak time: first flux maximum of the r band in FILE order, else over all rows (:331-338)
     if (warp == 0) {
@@ -493,30 +558,32 @@ int run_gp2d(const mlrn_store* s, double* out_dev, int* status_dev, cudaStream_t
   if (s->n_obj == 0) return MLRN_OK;
   const int T_need = (s->max_obs + TB - 1) / TB > 1 ? (s->max_obs + TB - 1) / TB : 1;
   const int T1 = T_need < T_SMEM_MAX ? T_need : T_SMEM_MAX;
+  const int grid = s->n_obj < s->sm_count ? s->n_obj : s->sm_count;
+  double* cache = nullptr;                              // s / exp(-s) of the current evaluation, per CTA (L2-resident)
+  MLRN_CUDA(cudaMallocAsync(&cache, sizeof(double) * 2 * (size_t)n_tiles(T_need) * TT * grid, st));
   {
     const size_t smem = gp_smem_bytes(T1, true);
     MLRN_CUDA(cudaFuncSetAttribute(k_gp2d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = s->n_obj < s->sm_count ? s->n_obj : s->sm_count;
     MLRN_CUDA(cudaMemsetAsync(s->ticket + 2, 0, 2 * sizeof(unsigned long long), st));
     k_gp2d<true><<<grid, GP_THREADS, smem, st>>>(s->seg_off, s->t, s->flux, s->err, s->rank, s->n_obj, T1, 0, T1 * TB,
-                                                 nullptr, s->ticket + 2, out_dev, status_dev);
+                                                 nullptr, cache, s->ticket + 2, out_dev, status_dev);
     MLRN_CUDA(cudaGetLastError());
     count_launch();
   }
   if (T_need > T_SMEM_MAX) {                            // long objects: tiles in global scratch
     const size_t smem = gp_smem_bytes(T_need, false);
     MLRN_CUDA(cudaFuncSetAttribute(k_gp2d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = s->n_obj < s->sm_count ? s->n_obj : s->sm_count;
     double* scratch = nullptr;
     const size_t per_cta = gp_tile_doubles(T_need) * sizeof(double);
     MLRN_CUDA(cudaMallocAsync(&scratch, per_cta * grid, st));
     k_gp2d<false><<<grid, GP_THREADS, smem, st>>>(s->seg_off, s->t, s->flux, s->err, s->rank, s->n_obj, T_need,
-                                                  T1 * TB + 1, T_need * TB, scratch, s->ticket + 3, out_dev, status_dev);
+                                                  T1 * TB + 1, T_need * TB, scratch, cache, s->ticket + 3, out_dev, status_dev);
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(scratch, st);
-    if (e != cudaSuccess) return cuda_fail(e, "k_gp2d<global> launch");
+    if (e != cudaSuccess) { cudaFreeAsync(cache, st); return cuda_fail(e, "k_gp2d<global> launch"); }
     count_launch();
   }
+  cudaFreeAsync(cache, st);
   return MLRN_OK;
 }
 

@@ -118,7 +118,7 @@ MLRN_FN void small_svd(double* a, const double* b, double* s, double* V, double*
       for (int q = p + 1; q < NP; ++q) {
         double al = 0.0, be = 0.0, ga = 0.0;
         for (int r = 0; r < NP; ++r) { double x = a[p * NP + r], y = a[q * NP + r]; al += x * x; be += y * y; ga += x * y; }
-        if (ga == 0.0 || fabs(ga) <= 1e-17 * sqrt(al * be)) continue;
+        if (ga == 0.0 || fabs(ga) <= 1.1e-16 * sqrt(al * be)) continue;   // columns orthogonal to working precision
         rotated = true;
         double zeta = (be - al) / (2.0 * ga);
         double t = ((zeta >= 0.0) ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));

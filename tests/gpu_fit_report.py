@@ -6,7 +6,7 @@ import numpy as np
 from fitparity import classify_bazin, classify_r2
 from mallorn_astrophysics_b200.store import LightCurveStore
 from mallorn_astrophysics_b200.synth import make_table
-for name in ("ref_sparse", "ref_dense", "ref_edge"):
+for name in (() if "nogolden" in sys.argv else ("ref_sparse", "ref_dense", "ref_edge")):
     g = np.load(os.path.join(ROOT, "tests", "golden", f"{name}.npz"))
     with LightCurveStore(g["obj"], g["band"], g["t"], g["flux"], g["err"], int(g["n_obj"])) as s:
         st = np.zeros((s.n_obj, 6, 2), np.int32)
@@ -19,7 +19,7 @@ import torch
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 table = make_table(n, config_index=3)
 with LightCurveStore.from_table(table) as s:
-    for m in ("bazin", "powerlaw") + (("gp2d",) if "gp2d" in sys.argv else ()):
+    for m in (() if "nofits" in sys.argv else ("bazin", "powerlaw")) + (("gp2d",) if "gp2d" in sys.argv else ()):
         out = torch.empty((n, {"bazin": 52, "powerlaw": 27, "gp2d": 27}[m]), dtype=torch.float64, device="cuda")
         s.features(m, out=out); torch.cuda.synchronize()
         t0 = time.perf_counter(); s.features(m, out=out); torch.cuda.synchronize(); dt = time.perf_counter() - t0
