@@ -1,0 +1,128 @@
+// fits_thread.cuh -- K4 with one THREAD per fit (trf_thread.cuh): the Bazin fit of one (object, band) and
+// the decline-model fit of one (object, band, model) as resumable jobs.  Same reference behaviour as
+// fits.cuh (bazin_fitting.py:63-179, scripts/train_v55_powerlaw.py:147-194); the band is read in place
+// from the packed store (time-sorted), nothing is staged.
+#pragma once
+#include "fits.cuh"
+#include "trf_thread.cuh"
+
+namespace mlrn {
+
+// k-th smallest (0-based) of a[0..n) by rank counting (ties broken by index); O(n^2) compares, no scratch
+MLRN_FN double kth_smallest(const double* a, int n, int k) {
+  for (int i = 0; i < n; ++i) {
+    const double v = a[i];
+    int rk = 0;
+    for (int j = 0; j < n; ++j) { const double u = a[j]; rk += (u < v) || (u == v && j < i); }
+    if (rk == k) return v;
+  }
+  return qnan();
+}
+MLRN_FN double median_unsorted(const double* a, int n) {
+  return (n & 1) ? kth_smallest(a, n, n >> 1) : 0.5 * (kth_smallest(a, n, (n >> 1) - 1) + kth_smallest(a, n, n >> 1));
+}
+
+struct BazinJob {
+  TrfThread<5, BazinModel> trf;
+  const double *t, *f, *e; int n;
+
+  // Returns true if the fit is running; otherwise `code` is final (skipped / bad input / infeasible start).
+  MLRN_FN bool init(const double* t_, const double* f_, const double* e_, int n_, int& code) {
+    t = t_; f = f_; e = e_; n = n_;
+    if (n < 5) { code = FIT_SKIPPED; return false; }                          // :76
+    bool bad = false; int pk = 0;
+    for (int i = 0; i < n; ++i) { bad = bad || !is_finite(t[i]) || !is_finite(f[i]); if (f[i] > f[pk]) pk = i; }
+    if (bad) { code = FIT_BAD_INPUT; return false; }
+    const double med = median_unsorted(f, n), mx = f[pk], dur = t[n - 1] - t[0];
+    const double x0[5] = {f[pk] - med, t[pk], dur * 0.2, dur * 0.3, med};     // :97-105
+    const double lo[5] = {0.0, t[0], 0.1, 0.1, -mx};                          // :114-118
+    const double hi[5] = {3.0 * mx, t[n - 1], dur, dur, 2.0 * mx};
+    code = trf.begin(BazinModel{t, f, e}, n, x0, lo, hi, 2000);
+    return code == TRF_RUNNING;
+  }
+  MLRN_FN int step() { return trf.step(); }
+  // out: 8 features (NaN unless status > 0)
+  MLRN_FN void finish(int status, double* out) const {
+    for (int k = 0; k < 8; ++k) out[k] = qnan();
+    if (status <= 0) return;
+    const double* x = trf.x;
+    const double A = clip(x[0], -1e6, 1e6), tr = clip(x[2], 0.1, 1e4), tf = clip(x[3], 0.1, 1e4), B = clip(x[4], -1e6, 1e6);
+    const double xc[5] = {A, x[1], tr, tf, B};
+    double chi = 0.0;
+    for (int i = 0; i < n; ++i) { const double sg = (e[i] > 0.0) ? e[i] : 1.0; const double r = (f[i] - bazin_value(t[i], xc)) / sg; chi += r * r; }
+    out[0] = A; out[1] = x[1]; out[2] = tr; out[3] = tf; out[4] = B;
+    out[5] = clip(chi / (double)(n - 5), 0.0, 1e6);
+    out[6] = clip(tr / (tf + 1e-6), 0.0, 100.0);
+    out[7] = clip(A + B, -1e6, 1e6);
+  }
+};
+
+// decline models on the post-peak suffix of a time-sorted band: x_i = t_i - t_peak, y_i = f_i
+struct PowerModelT {
+  const double* t; const double* y; double pt, k;
+  MLRN_FN_FORCE double value(int i, const double* p) const { return p[0] * pow(fmax((t[i] - pt) - p[1], 0.1), k); }
+  MLRN_FN_FORCE double resid(int i, const double* p) const { return value(i, p) - y[i]; }
+};
+struct ExpModelT {
+  const double* t; const double* y; double pt, k;
+  MLRN_FN_FORCE double value(int i, const double* p) const { return p[0] * exp(-fmax((t[i] - pt) - p[2], 0.0) / p[1]); }
+  MLRN_FN_FORCE double resid(int i, const double* p) const { return value(i, p) - y[i]; }
+};
+struct LinModelT {
+  const double* t; const double* y; double pt, k;
+  MLRN_FN_FORCE double value(int i, const double* p) const { return p[0] - p[1] * fmax((t[i] - pt) - p[2], 0.0); }
+  MLRN_FN_FORCE double resid(int i, const double* p) const { return value(i, p) - y[i]; }
+};
+
+// KIND 0: power law with fixed index k (NP = 2); 1: exponential (NP = 3); 2: linear (NP = 3)
+template <int KIND> struct DeclineTraits;
+template <> struct DeclineTraits<0> { static constexpr int NP = 2; using Model = PowerModelT; };
+template <> struct DeclineTraits<1> { static constexpr int NP = 3; using Model = ExpModelT; };
+template <> struct DeclineTraits<2> { static constexpr int NP = 3; using Model = LinModelT; };
+
+template <int KIND>
+struct DeclineJob {
+  static constexpr int NP = DeclineTraits<KIND>::NP;
+  using Model = typename DeclineTraits<KIND>::Model;
+  TrfThread<NP, Model> trf;
+  Model mdl; int m; double ss_tot;
+
+  MLRN_FN bool init(const double* t, const double* f, int n, double kpow, int& code) {
+    if (n < 5) { code = FIT_SKIPPED; return false; }                          // :150
+    int pk = 0;
+    for (int i = 1; i < n; ++i) if (f[i] > f[pk]) pk = i;
+    const double pt = t[pk], pf = f[pk];
+    int start = n;
+    for (int i = n - 1; i >= 0 && t[i] > pt; --i) start = i;                  // time-sorted: t > t_peak is a suffix
+    m = n - start;
+    if (m < 3) { code = FIT_SKIPPED; return false; }                          // :162
+    const double* ts = t + start; const double* ys = f + start;
+    bool bad = false; double sum = 0.0;
+    for (int i = 0; i < m; ++i) { bad = bad || !is_finite(ts[i] - pt) || !is_finite(ys[i]); sum += ys[i]; }
+    if (bad) { code = FIT_BAD_INPUT; return false; }
+    const double ymean = sum / (double)m;
+    ss_tot = 0.0;
+    for (int i = 0; i < m; ++i) { const double d = ys[i] - ymean; ss_tot += d * d; }
+    mdl = Model{ts, ys, pt, kpow};
+    double x0[3], lo[3], hi[3];
+    if (KIND == 0) { x0[0] = pf; x0[1] = 0.0; lo[0] = 0.0; lo[1] = -10.0; hi[0] = 1e6; hi[1] = 10.0; }
+    else if (KIND == 1) { x0[0] = pf; x0[1] = 30.0; x0[2] = 0.0; lo[0] = 0.0; lo[1] = 1.0; lo[2] = -10.0; hi[0] = 1e6; hi[1] = 500.0; hi[2] = 10.0; }
+    else { x0[0] = pf; x0[1] = 1.0; x0[2] = 0.0; lo[0] = 0.0; lo[1] = 0.0; lo[2] = -10.0; hi[0] = 1e6; hi[1] = 100.0; hi[2] = 10.0; }
+    code = trf.begin(mdl, m, x0, lo, hi, 1000);
+    return code == TRF_RUNNING;
+  }
+  MLRN_FN int step() { return trf.step(); }
+  MLRN_FN double finish(int status) const {
+    if (status <= 0) return qnan();
+    double ss = 0.0;
+    for (int i = 0; i < m; ++i) { const double r = mdl.y[i] - mdl.value(i, trf.x); ss += r * r; }
+    return (ss_tot > 0.0) ? 1.0 - ss / ss_tot : 0.0;                           // :186-189
+  }
+};
+
+MLRN_FN double decline_index(int q) {                                          // MODELS order (:135-145)
+  const double kk[7] = {-5.0 / 3.0, -1.0, -1.5, -2.0, -2.5, -3.0, -0.5};
+  return kk[q];
+}
+
+}  // namespace mlrn

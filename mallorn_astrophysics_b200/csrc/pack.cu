@@ -296,7 +296,7 @@ int pack_device(mlrn_store* s, int64_t n_rows, const int32_t* obj, const uint8_t
   MLRN_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 4, st));
   MLRN_CUDA(cudaMalloc(&s->seg_off, sizeof(long long) * (size_t)(n_seg + 1)));
   MLRN_CUDA(cudaMalloc(&s->seg_meta, sizeof(int32_t) * (size_t)(n_obj > 0 ? n_obj : 1) * MLRN_SEGMETA_COLS));
-  MLRN_CUDA(cudaMalloc(&s->ticket, sizeof(unsigned long long) * 4));
+  MLRN_CUDA(cudaMalloc(&s->ticket, sizeof(unsigned long long) * 8));
 
   const int row_grid = (int)((n_rows + 255) / 256 < (int64_t)s->sm_count * 16 ? (n_rows + 255) / 256 : (int64_t)s->sm_count * 16);
   if (n_rows > 0) { k_count<<<row_grid > 0 ? row_grid : 1, 256, 0, st>>>(obj, band, n_rows, n_obj, seg_cnt); count_launch(); }

@@ -17,7 +17,7 @@ struct mlrn_store {
   double* err = nullptr;
   unsigned short* rank = nullptr;   // [n_rows]
   int32_t* seg_meta = nullptr;      // [n_obj*22]
-  unsigned long long* ticket = nullptr;   // [4] work counters of the fit / GP passes (one per pass)
+  unsigned long long* ticket = nullptr;   // [8] work counters of the fit / GP passes (one per launch)
 };
 
 namespace mlrn {

@@ -33,7 +33,7 @@ def launches(path):
         except ValueError:
             continue
         name = re.sub(r"\(.*", "", r[ki])
-        name = re.sub(r"^void |mlrn::|<unnamed>::", "", name)
+        name = re.sub(r"^.*unnamed>::|^void |mlrn::", "", name)
         a = agg.setdefault(name, [0, 0.0])
         a[0] += 1; a[1] += v
     tot = sum(v for _, v in agg.values())

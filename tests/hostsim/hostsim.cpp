@@ -13,6 +13,7 @@
 #include "physics.cuh"
 #include "fits.cuh"
 #include "gp_host.hpp"
+#include "fits_thread.cuh"
 
 using namespace mlrn;
 
@@ -23,6 +24,14 @@ struct Scratch {
   explicit Scratch(int cap) : t(cap), f(cap), e(cap), sa(cap), sb(cap), sc(cap), sd(cap), row(512), rank(cap) {}
 };
 }  // namespace
+
+template <int KIND>
+static void hs_decline_one(const double* t, const double* f, int n, double k, double* out, int* status) {
+  DeclineJob<KIND> job; int code;
+  if (job.init(t, f, n, k, code)) { while ((code = job.step()) == TRF_RUNNING) {} }
+  *out = job.finish(code);
+  if (status) { status[0] = code; status[1] = (code == FIT_SKIPPED || code == FIT_BAD_INPUT) ? 0 : job.trf.nfev; }
+}
 
 extern "C" {
 
@@ -85,6 +94,41 @@ int hs_powerlaw(long long n_obj, const long long* seg_off, const double* t, cons
     powerlaw_row(tm, v, s.sa.data(), s.sb.data(), work.data(), MAX_OBS, s.row.data(), status ? status + o * 54 : nullptr);
     std::memcpy(out + o * POWERLAW_COLS, s.row.data(), sizeof(double) * POWERLAW_COLS);
   }
+  return 0;
+}
+
+// one-thread-per-fit variants (trf_thread.cuh / fits_thread.cuh)
+int hs_bazin_t(long long n_obj, const long long* seg_off, const double* t, const double* f, const double* e,
+               const unsigned short* rank, double* out, int* status) {
+  HostTeam tm;
+  for (long long o = 0; o < n_obj; ++o) {
+    double* row = out + o * BAZIN_COLS;
+    for (int b = 0; b < N_BAND; ++b) {
+      const long long lo = seg_off[o * N_SEG + b];
+      const int n = (int)(seg_off[o * N_SEG + b + 1] - lo);
+      BazinJob job; int code;
+      if (job.init(t + lo, f + lo, e + lo, n, code)) { while ((code = job.step()) == TRF_RUNNING) {} }
+      job.finish(code, row + 8 * b);
+      if (status) { status[o * 12 + 2 * b] = code; status[o * 12 + 2 * b + 1] = (code == FIT_SKIPPED || code == FIT_BAD_INPUT) ? 0 : job.trf.nfev; }
+    }
+    bazin_tail(tm, row);
+  }
+  return 0;
+}
+
+int hs_powerlaw_t(long long n_obj, const long long* seg_off, const double* t, const double* f, const double* e,
+                  const unsigned short* rank, double* out, int* status) {
+  const int bands[3] = {BG, BR, BI};
+  for (long long o = 0; o < n_obj; ++o)
+    for (int j = 0; j < 3; ++j) {
+      const long long lo = seg_off[o * N_SEG + bands[j]];
+      const int n = (int)(seg_off[o * N_SEG + bands[j] + 1] - lo);
+      double* row = out + o * POWERLAW_COLS + 9 * j;
+      int* st = status ? status + o * 54 + 18 * j : nullptr;
+      for (int q = 0; q < 7; ++q) hs_decline_one<0>(t + lo, f + lo, n, decline_index(q), row + q, st ? st + 2 * q : nullptr);
+      hs_decline_one<1>(t + lo, f + lo, n, 0.0, row + 7, st ? st + 14 : nullptr);
+      hs_decline_one<2>(t + lo, f + lo, n, 0.0, row + 8, st ? st + 16 : nullptr);
+    }
   return 0;
 }
 
