@@ -34,7 +34,7 @@ constexpr int TB = 16;                 // tile edge
 constexpr int TT = TB * TB;            // doubles per tile
 constexpr int GP_COLS = 27;
 constexpr int T_SMEM_MAX = 12;         // 78 tiles + V buffer + vectors < 227 KB  (N <= 192 in shared memory)
-constexpr int VLD = 18;                // column stride of a V tile (padding against bank conflicts)
+constexpr int VLD = 20;                // k-row stride of a V tile: 8-word skew per row keeps the DMMA fragment loads conflict-free
 constexpr int VT = TB * VLD;           // doubles per V tile
 constexpr double GP_TINY = 1.25e-12;   // george's frozen white-noise floor
 constexpr double LOG_2PI = 1.8378770664093453;
@@ -87,52 +87,39 @@ __device__ __forceinline__ KernelPars unpack(const double* p) {
 // over the shared-memory banks, and (r, r+1) pairs with r even stay one aligned double2
 __device__ __forceinline__ int tix(int r, int c) { return c * TB + (r ^ (c & 14)); }
 
-// Pivot tile k: L = chol(A_kk) held one row per lane in registers (columns broadcast by shuffle), then
-// L^-1 (one column per lane), w = L^-1 b_k.  One warp.  Results in S.Li/LiT/w[buf]; ln|K| via the product of pivots.
+// Pivot tile k, one warp.  Lanes 0..15 hold one row of A_kk each and turn it into L = chol(A_kk) (right-
+// looking, the column being eliminated is broadcast by shuffle); lanes 16..31 hold one column of L^-1 each and
+// ride on the SAME broadcasts: forward substitution of column j needs exactly L[c2][c] x_c, the term the
+// Cholesky update multiplies by L[r][c].  Then w = L^-1 b_k.  Results in S.Li / S.LiT / S.w [buf];
+// ln|K| from the product of the pivots.
 __device__ __forceinline__ void pivot_warp(const GpShared& S, int k, int buf, double& quad, double& logdet, int& fail) {
   const int lane = threadIdx.x & 31, r = lane & 15;
+  const bool lower = lane < TB;
   const double* A = tile_ptr(S, k, k);
-  double row[TB], rinv[TB];
+  double val[TB];
 #pragma unroll
-  for (int c = 0; c < TB; ++c) row[c] = A[tix(r, c)];
+  for (int c = 0; c < TB; ++c) val[c] = lower ? A[tix(r, c)] : ((c == r) ? 1.0 : 0.0);
   double prod = 1.0; bool bad = false;
 #pragma unroll
   for (int c = 0; c < TB; ++c) {
-    const double piv = __shfl_sync(FULLMASK, row[c], c);
+    const double piv = __shfl_sync(FULLMASK, val[c], c);
     bad = bad || !(piv > 0.0);
     const double ri = rsqrt(piv);
-    rinv[c] = ri; prod *= piv;
-    const double l = (r == c) ? piv * ri : row[c] * ri;
-    row[c] = l;
+    prod *= piv;
+    const double mult = val[c] * ri;       // L[r][c] on the lower lanes, (L^-1)[c][j] on the upper lanes
+    val[c] = mult;
 #pragma unroll
-    for (int c2 = c + 1; c2 < TB; ++c2) row[c2] -= l * __shfl_sync(FULLMASK, l, c2);
+    for (int c2 = c + 1; c2 < TB; ++c2) val[c2] -= mult * __shfl_sync(FULLMASK, mult, c2);
   }
-  if (lane < TB) {
+  if (!lower) {
 #pragma unroll
-    for (int c = 0; c < TB; ++c) S.Lc[c * TB + r] = row[c];          // L[r][c] at c*16 + r
-  }
-  __syncwarp();
-  {
-    const int j = r;                       // this lane's column of L^-1
-    double acc[TB], x[TB];
-#pragma unroll
-    for (int q = 0; q < TB; ++q) acc[q] = (q == j) ? 1.0 : 0.0;
-#pragma unroll
-    for (int m = 0; m < TB; ++m) {
-      x[m] = (m >= j) ? acc[m] * rinv[m] : 0.0;
-#pragma unroll
-      for (int q = m + 1; q < TB; ++q) acc[q] -= S.Lc[m * TB + q] * x[m];
-    }
-    if (lane < TB) {
-#pragma unroll
-      for (int q = 0; q < TB; ++q) { S.Li[buf * TT + q * TB + j] = x[q]; S.LiT[buf * VT + j * VLD + q] = x[q]; }   // Li[q][j]
-    }
+    for (int q = 0; q < TB; ++q) { S.Li[buf * TT + q * TB + r] = val[q]; S.LiT[buf * VT + r * VLD + q] = val[q]; }   // Li[q][j], j = r
   }
   __syncwarp();
   double wq = 0.0;
-  if (lane < TB) {
+  if (lower) {
     double s = 0.0;
-    for (int c = 0; c <= r; ++c) s += S.Li[buf * TT + r * TB + c] * S.sb[k * TB + c];
+    for (int c = 0; c <= r; ++c) s += S.LiT[buf * VT + c * VLD + r] * S.sb[k * TB + c];       // Li[r][c]
     S.w[buf * TB + r] = s; wq = s * s;
   }
 #pragma unroll
@@ -142,87 +129,95 @@ __device__ __forceinline__ void pivot_warp(const GpShared& S, int k, int buf, do
   __syncwarp();
 }
 
-// ---- warp-level 16x16x16 FP64 products; lane (g = lane % 8, h = lane / 8) owns rows 2g..2g+1, cols 4h..4h+3
-#define MLRN_FMA8(acc, a, b0, b1)                                                                     \
-  acc[0][0] += a.x * b0.x; acc[0][1] += a.x * b0.y; acc[0][2] += a.x * b1.x; acc[0][3] += a.x * b1.y;  \
-  acc[1][0] += a.y * b0.x; acc[1][1] += a.y * b0.y; acc[1][2] += a.y * b1.x; acc[1][3] += a.y * b1.y;
+// ---- warp-level 16x16x16 FP64 products on the FP64 tensor-core path (mma.sync m8n8k4, "DMMA"):
+// per k-step of 4 a lane loads ONE double per operand fragment instead of the 6 a register-blocked FMA
+// loop needs, which takes the shared-memory pipe off the critical path.  Fragment layout (PTX ISA):
+//   A (8x4, row)  lane l holds A[l/4][l%4]     B (4x8, col)  lane l holds B[l%4][l/4]
+//   C/D (8x8)     lane l holds C[l/4][2*(l%4)], C[l/4][2*(l%4)+1]
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
 
-// C(i, j) -= Vi Vj^T
-__device__ __forceinline__ void tile_update(double* __restrict__ C, const double* __restrict__ Vi, const double* __restrict__ Vj) {
-  const int lane = threadIdx.x & 31, g = lane & 7, h = lane >> 3;
-  double acc[2][4] = {};
+// acc[ri][ci][0..1] += sum_m A(8ri + l/4, m) * B(m, 8ci + 2(l%4) + {0,1}) over m = 0..15, where the operands
+// are given K-MAJOR: Ak[m*lda + row], Bk[m*ldb + col]
+__device__ __forceinline__ void dmma_16x16x16(double (&acc)[2][2][2], const double* __restrict__ Ak, int lda,
+                                              const double* __restrict__ Bk, int ldb, bool negate_a) {
+  const int lane = threadIdx.x & 31, lr = lane >> 2, lk = lane & 3;
 #pragma unroll
-  for (int m = 0; m < TB; ++m) {
-    const double2 a = *reinterpret_cast<const double2*>(Vi + m * VLD + 2 * g);
-    const double2 b0 = *reinterpret_cast<const double2*>(Vj + m * VLD + 4 * h);
-    const double2 b1 = *reinterpret_cast<const double2*>(Vj + m * VLD + 4 * h + 2);
-    MLRN_FMA8(acc, a, b0, b1)
-  }
-#pragma unroll
-  for (int cc = 0; cc < 4; ++cc) {
-    const int c = 4 * h + cc;
-    double2* p = reinterpret_cast<double2*>(C + c * TB + ((2 * g) ^ (c & 14)));
-    double2 v = *p;
-    v.x -= acc[0][cc]; v.y -= acc[1][cc];
-    *p = v;
+  for (int ks = 0; ks < 4; ++ks) {
+    const int m = 4 * ks + lk;
+    double a0 = Ak[m * lda + lr], a1 = Ak[m * lda + 8 + lr];
+    const double b0 = Bk[m * ldb + lr], b1 = Bk[m * ldb + 8 + lr];
+    if (negate_a) { a0 = -a0; a1 = -a1; }
+    dmma(acc[0][0][0], acc[0][0][1], a0, b0);
+    dmma(acc[0][1][0], acc[0][1][1], a0, b1);
+    dmma(acc[1][0][0], acc[1][0][1], a1, b0);
+    dmma(acc[1][1][0], acc[1][1][1], a1, b1);
   }
 }
 
-// V = X Li^T, X = block (i, k) of the symmetric matrix: tile(i, k) if i > k, tile(k, i)^T if i < k
+// C(i, j) -= Vi Vj^T        (C swizzled tile, V tiles k-major with stride VLD)
+__device__ __forceinline__ void tile_update(double* __restrict__ C, const double* __restrict__ Vi, const double* __restrict__ Vj) {
+  const int lane = threadIdx.x & 31, lr = lane >> 2, lc = 2 * (lane & 3);
+  double acc[2][2][2];
+#pragma unroll
+  for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+    for (int ci = 0; ci < 2; ++ci)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) { const int r = 8 * ri + lr, c = 8 * ci + lc + e; acc[ri][ci][e] = C[tix(r, c)]; }
+  dmma_16x16x16(acc, Vi, VLD, Vj, VLD, true);
+#pragma unroll
+  for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+    for (int ci = 0; ci < 2; ++ci)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) { const int r = 8 * ri + lr, c = 8 * ci + lc + e; C[tix(r, c)] = acc[ri][ci][e]; }
+}
+
+// V = X Li^T, X = block (i, k) of the symmetric matrix: tile(i, k) if i > k, tile(k, i)^T if i < k.
+// V[r][c] = sum_m X[r][m] Li[c][m]: A k-major = X[m][r] (column m of X), B k-major = LiT[m*VLD + c].
 __device__ __forceinline__ void tile_scale(double* __restrict__ V, const double* __restrict__ X, bool transposed,
                                            const double* __restrict__ LiT) {
-  const int lane = threadIdx.x & 31, g = lane & 7, h = lane >> 3;
-  double acc[2][4] = {};
-  if (!transposed) {
+  const int lane = threadIdx.x & 31, lr = lane >> 2, lk = lane & 3, lc = 2 * lk;
+  double acc[2][2][2] = {};
 #pragma unroll
-    for (int m = 0; m < TB; ++m) {
-      const double2 a = *reinterpret_cast<const double2*>(X + m * TB + ((2 * g) ^ (m & 14)));
-      const double2 b0 = *reinterpret_cast<const double2*>(LiT + m * VLD + 4 * h);
-      const double2 b1 = *reinterpret_cast<const double2*>(LiT + m * VLD + 4 * h + 2);
-      MLRN_FMA8(acc, a, b0, b1)
-    }
-  } else {
-#pragma unroll
-    for (int m = 0; m < TB; ++m) {
-      double2 a;
-      a.x = X[(2 * g) * TB + (m ^ (2 * g))];            // element (m, 2g) of the stored tile
-      a.y = X[(2 * g + 1) * TB + (m ^ (2 * g))];
-      const double2 b0 = *reinterpret_cast<const double2*>(LiT + m * VLD + 4 * h);
-      const double2 b1 = *reinterpret_cast<const double2*>(LiT + m * VLD + 4 * h + 2);
-      MLRN_FMA8(acc, a, b0, b1)
-    }
+  for (int ks = 0; ks < 4; ++ks) {
+    const int m = 4 * ks + lk;
+    double a0, a1;
+    if (!transposed) { a0 = X[tix(lr, m)]; a1 = X[tix(8 + lr, m)]; }          // element (r, m) of tile(i, k)
+    else { a0 = X[tix(m, lr)]; a1 = X[tix(m, 8 + lr)]; }                       // element (m, r) of tile(k, i)
+    const double b0 = LiT[m * VLD + lr], b1 = LiT[m * VLD + 8 + lr];
+    dmma(acc[0][0][0], acc[0][0][1], a0, b0);
+    dmma(acc[0][1][0], acc[0][1][1], a0, b1);
+    dmma(acc[1][0][0], acc[1][0][1], a1, b0);
+    dmma(acc[1][1][0], acc[1][1][1], a1, b1);
   }
 #pragma unroll
-  for (int cc = 0; cc < 4; ++cc)
-    *reinterpret_cast<double2*>(V + (4 * h + cc) * VLD + 2 * g) = make_double2(acc[0][cc], acc[1][cc]);
+  for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+    for (int ci = 0; ci < 2; ++ci)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) V[(8 * ci + lc + e) * VLD + 8 * ri + lr] = acc[ri][ci][e];
 }
 
-// block (i, k) <- V Li, written to tile(i, k) or transposed into tile(k, i)
+// block (i, k) <- V Li, written to tile(i, k) or transposed into tile(k, i).
+// Z[r][c] = sum_m V[r][m] Li[m][c]: A k-major = V[m*VLD + r], B k-major = Li[m*16 + c] (row-major Li).
 __device__ __forceinline__ void tile_finalise(double* __restrict__ Tl, bool transposed, const double* __restrict__ V,
                                               const double* __restrict__ Li) {
-  const int lane = threadIdx.x & 31, g = lane & 7, h = lane >> 3;
-  double acc[2][4] = {};
+  const int lane = threadIdx.x & 31, lr = lane >> 2, lc = 2 * (lane & 3);
+  double acc[2][2][2] = {};
+  dmma_16x16x16(acc, V, VLD, Li, TB, false);
 #pragma unroll
-  for (int m = 0; m < TB; ++m) {
-    const double2 a = *reinterpret_cast<const double2*>(V + m * VLD + 2 * g);
-    const double2 b0 = *reinterpret_cast<const double2*>(Li + m * TB + 4 * h);
-    const double2 b1 = *reinterpret_cast<const double2*>(Li + m * TB + 4 * h + 2);
-    MLRN_FMA8(acc, a, b0, b1)
-  }
-  if (!transposed) {
+  for (int ri = 0; ri < 2; ++ri)
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      const int c = 4 * h + cc;
-      *reinterpret_cast<double2*>(Tl + c * TB + ((2 * g) ^ (c & 14))) = make_double2(acc[0][cc], acc[1][cc]);
-    }
-  } else {
+    for (int ci = 0; ci < 2; ++ci)
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {                    // stored element (row c, col r) for r = 2g + rr
-      double* base = Tl + (2 * g + rr) * TB;
-      *reinterpret_cast<double2*>(base + ((4 * h) ^ (2 * g))) = make_double2(acc[rr][0], acc[rr][1]);
-      *reinterpret_cast<double2*>(base + ((4 * h + 2) ^ (2 * g))) = make_double2(acc[rr][2], acc[rr][3]);
-    }
-  }
+      for (int e = 0; e < 2; ++e) {
+        const int r = 8 * ri + lr, c = 8 * ci + lc + e;
+        Tl[transposed ? tix(c, r) : tix(r, c)] = acc[ri][ci][e];
+      }
 }
 
 // -ln L and its gradient at p.  Leaves alpha in S.sb[0..n).  Result broadcast to every thread.
