@@ -68,8 +68,10 @@ int mlrn_store_info(const mlrn_store* s, int64_t* n_rows, int32_t* n_obj, int32_
  * then peak_band (statistical.py:217-222).  Bit-exact contract. */
 int mlrn_store_segments(const mlrn_store* s, int32_t* out_host);
 /* packed columns to HOST memory (any pointer may be NULL): seg_off int64[n_obj*7+1],
- * t/flux/err float64[n_rows], rank uint16[n_rows] */
-int mlrn_store_export(const mlrn_store* s, int64_t* seg_off, double* t, double* flux, double* err, uint16_t* rank);
+ * t/flux/err float64[n_rows], rank / trank uint16[n_rows] (position inside the object in file order /
+ * in (time, file rank) order over all bands) */
+int mlrn_store_export(const mlrn_store* s, int64_t* seg_off, double* t, double* flux, double* err, uint16_t* rank,
+                      uint16_t* trank);
 
 /* Feature passes.  out: float64 [n_obj, MLRN_*_COLS]. */
 int mlrn_stat(const mlrn_store* s, double* out, int out_on_device, void* stream);

@@ -46,7 +46,7 @@ def lib() -> C.CDLL:
     L.mlrn_store_destroy.argtypes = [vp]
     L.mlrn_store_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]
     L.mlrn_store_segments.argtypes = [vp, vp]
-    L.mlrn_store_export.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.mlrn_store_export.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     for name in ("mlrn_stat", "mlrn_color", "mlrn_shape", "mlrn_tde"):
         if hasattr(L, name):
             getattr(L, name).argtypes = [vp, vp, C.c_int, vp]

@@ -137,7 +137,7 @@ int mlrn_store_create(int device, int64_t n_rows, int32_t n_obj, const int32_t* 
 int mlrn_store_destroy(mlrn_store* s) {
   if (!s) return MLRN_OK;
   DevGuard g(s->device);
-  cudaFree(s->seg_off); cudaFree(s->t); cudaFree(s->flux); cudaFree(s->err); cudaFree(s->rank); cudaFree(s->seg_meta); cudaFree(s->ticket);
+  cudaFree(s->seg_off); cudaFree(s->t); cudaFree(s->flux); cudaFree(s->err); cudaFree(s->rank); cudaFree(s->trank); cudaFree(s->seg_meta); cudaFree(s->ticket);
   delete s;
   return MLRN_OK;
 }
@@ -158,7 +158,8 @@ int mlrn_store_segments(const mlrn_store* s, int32_t* out_host) {
   return MLRN_OK;
 }
 
-int mlrn_store_export(const mlrn_store* s, int64_t* seg_off, double* t, double* flux, double* err, uint16_t* rank) {
+int mlrn_store_export(const mlrn_store* s, int64_t* seg_off, double* t, double* flux, double* err, uint16_t* rank,
+                      uint16_t* trank) {
   if (!s) { set_error("null store"); return MLRN_EINVAL; }
   DevGuard g(s->device);
   MLRN_CUDA(cudaDeviceSynchronize());
@@ -168,6 +169,7 @@ int mlrn_store_export(const mlrn_store* s, int64_t* seg_off, double* t, double* 
   if (flux && n) MLRN_CUDA(cudaMemcpy(flux, s->flux, 8 * n, cudaMemcpyDeviceToHost));
   if (err && n) MLRN_CUDA(cudaMemcpy(err, s->err, 8 * n, cudaMemcpyDeviceToHost));
   if (rank && n) MLRN_CUDA(cudaMemcpy(rank, s->rank, 2 * n, cudaMemcpyDeviceToHost));
+  if (trank && n) MLRN_CUDA(cudaMemcpy(trank, s->trank, 2 * n, cudaMemcpyDeviceToHost));
   return MLRN_OK;
 }
 

@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(ARR_WARPS * 32)
 k_arrange(const uint8_t* __restrict__ band_in, const double* __restrict__ t_in, const double* __restrict__ f_in,
           const double* __restrict__ e_in, const int* __restrict__ rowid, const long long* __restrict__ seg_off,
           int n_obj, int np, double* __restrict__ t_out, double* __restrict__ f_out, double* __restrict__ e_out,
-          unsigned short* __restrict__ rank_out, int* __restrict__ seg_meta, int* __restrict__ err_flag) {
+          unsigned short* __restrict__ rank_out, unsigned short* __restrict__ trank_out, int* __restrict__ seg_meta, int* __restrict__ err_flag) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char* base = smem + (size_t)warp * arrange_bytes_per_warp(np);
@@ -244,6 +244,7 @@ k_arrange(const uint8_t* __restrict__ band_in, const double* __restrict__ t_in, 
         f_out[gbase + dest] = ff[src];
         e_out[gbase + dest] = e_in[r];
         rank_out[gbase + dest] = (unsigned short)src;
+        trank_out[gbase + dest] = (unsigned short)i;
         fs[dest] = ff[src];
       }
     }
@@ -326,6 +327,7 @@ int pack_device(mlrn_store* s, int64_t n_rows, const int32_t* obj, const uint8_t
   MLRN_CUDA(cudaMalloc(&s->flux, sizeof(double) * nr));
   MLRN_CUDA(cudaMalloc(&s->err, sizeof(double) * nr));
   MLRN_CUDA(cudaMalloc(&s->rank, sizeof(unsigned short) * nr));
+  MLRN_CUDA(cudaMalloc(&s->trank, sizeof(unsigned short) * nr));
   MLRN_CUDA(cudaMallocAsync(&rowid, sizeof(int) * nr, st));
   if (n_rows > 0 && n_obj > 0) {
     k_scatter<<<row_grid > 0 ? row_grid : 1, 256, 0, st>>>(obj, n_rows, n_obj, s->seg_off, cursor, rowid);
@@ -336,7 +338,7 @@ int pack_device(mlrn_store* s, int64_t n_rows, const int32_t* obj, const uint8_t
     const int cap = s->sm_count * 8;
     if (grid > cap) grid = cap;
     k_arrange<<<grid, ARR_WARPS * 32, smem, st>>>(band, t, flux, err, rowid, s->seg_off, n_obj, np, s->t, s->flux,
-                                                   s->err, s->rank, s->seg_meta, flags + 1);
+                                                   s->err, s->rank, s->trank, s->seg_meta, flags + 1);
     count_launch(2);
   }
   MLRN_CUDA(cudaGetLastError());

@@ -83,7 +83,8 @@ int launch_pass(const mlrn_store* s, const double* z, double* out, cudaStream_t 
 
 }  // namespace
 
-int run_stat(const mlrn_store* s, double* out_dev, cudaStream_t st) { return launch_pass<PASS_STAT>(s, nullptr, out_dev, st); }
+// the moment pass proper lives in stat_fast.cu; this generic instantiation is kept as a cross-check
+int run_stat_generic(const mlrn_store* s, double* out_dev, cudaStream_t st) { return launch_pass<PASS_STAT>(s, nullptr, out_dev, st); }
 int run_color(const mlrn_store* s, double* out_dev, cudaStream_t st) { return launch_pass<PASS_COLOR>(s, nullptr, out_dev, st); }
 int run_shape(const mlrn_store* s, double* out_dev, cudaStream_t st) { return launch_pass<PASS_SHAPE>(s, nullptr, out_dev, st); }
 int run_tde(const mlrn_store* s, double* out_dev, cudaStream_t st) { return launch_pass<PASS_TDE>(s, nullptr, out_dev, st); }

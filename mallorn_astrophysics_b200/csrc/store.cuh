@@ -15,7 +15,8 @@ struct mlrn_store {
   double* t = nullptr;              // [n_rows]
   double* flux = nullptr;
   double* err = nullptr;
-  unsigned short* rank = nullptr;   // [n_rows]
+  unsigned short* rank = nullptr;   // [n_rows] position of the row inside its object in FILE order
+  unsigned short* trank = nullptr;  // [n_rows] position inside its object in (time, file rank) order over ALL bands
   int32_t* seg_meta = nullptr;      // [n_obj*22]
   unsigned long long* ticket = nullptr;   // [8] work counters of the fit / GP passes (one per launch)
 };

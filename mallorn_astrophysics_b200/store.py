@@ -88,9 +88,10 @@ class LightCurveStore:
         seg = np.empty(self.n_obj * _native.N_SEG + 1, dtype=np.int64)
         t, f, e = (np.empty(self.n_rows, dtype=np.float64) for _ in range(3))
         rank = np.empty(self.n_rows, dtype=np.uint16)
+        trank = np.empty(self.n_rows, dtype=np.uint16)
         _native.check(_native.lib().mlrn_store_export(self._h, seg.ctypes.data, t.ctypes.data, f.ctypes.data,
-                                                      e.ctypes.data, rank.ctypes.data), "mlrn_store_export")
-        return {"seg_off": seg, "t": t, "flux": f, "err": e, "rank": rank}
+                                                      e.ctypes.data, rank.ctypes.data, trank.ctypes.data), "mlrn_store_export")
+        return {"seg_off": seg, "t": t, "flux": f, "err": e, "rank": rank, "trank": trank}
 
     def present(self) -> np.ndarray:
         """Indices of objects that have at least one observation."""

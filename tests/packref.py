@@ -21,5 +21,11 @@ def pack_reference(obj, band, t, flux, err, n_obj):
     seg_off = np.zeros(n_obj * N_SEG + 1, dtype=np.int64)
     np.cumsum(counts, out=seg_off[1:])
     rows = keep[final]
+    # time rank inside the object: position in (time, file rank) order over all bands
+    torder = np.lexsort((rank, t[keep], o))
+    trank = np.empty(len(keep), dtype=np.int64)
+    so2 = o[torder]
+    trank[torder] = np.arange(len(keep)) - np.searchsorted(so2, so2, side="left")
     return {"seg_off": seg_off, "t": np.ascontiguousarray(t[rows]), "flux": np.ascontiguousarray(flux[rows]),
-            "err": np.ascontiguousarray(err[rows]), "rank": rank[final].astype(np.uint16), "row": rows}
+            "err": np.ascontiguousarray(err[rows]), "rank": rank[final].astype(np.uint16),
+            "trank": trank[final].astype(np.uint16), "row": rows}

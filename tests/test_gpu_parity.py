@@ -39,6 +39,7 @@ def test_pack_is_bit_exact(golden, fixture):
     for k in ("t", "flux", "err"):
         assert np.array_equal(got[k].view(np.uint64), want[k].view(np.uint64)), k
     assert np.array_equal(got["rank"], want["rank"])
+    assert np.array_equal(got["trank"], want["trank"])
     present, meta = run_module("segments", g["obj"], g["band"], g["t"], g["flux"], g["err"], n_obj)
     assert np.array_equal(seg[present].astype(np.int64), meta)
     absent = np.setdiff1d(np.arange(n_obj), present)
