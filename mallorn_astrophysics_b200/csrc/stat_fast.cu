@@ -34,30 +34,27 @@ __device__ __forceinline__ double wmax(double v) {
   return v;
 }
 
-// ascending bitonic sort of NR*32 keys, element e = a*32 + lane lives in v[a] of `lane`
+// ascending bitonic sort of NR*32 keys, element e = a*32 + lane lives in v[a] of `lane`.  The (k, j) loops stay
+// rolled on purpose: fully unrolled, the network of the two instantiations pushed the kernel past the
+// instruction cache (ncu: 33 % of stall samples were "no instruction").
 template <int NR>
 __device__ __forceinline__ void reg_bitonic_sort(double (&v)[NR], int lane) {
-#pragma unroll
+#pragma unroll 1
   for (int k = 2; k <= 32 * NR; k <<= 1) {
-#pragma unroll
+#pragma unroll 1
     for (int j = k >> 1; j > 0; j >>= 1) {
-      if (j >= 32) {
-        const int jr = j >> 5;
-#pragma unroll
-        for (int a = 0; a < NR; ++a) {
-          if ((a & jr) == 0) {
-            const bool up = (((a << 5) | lane) & k) == 0;
-            const double lo = fmin(v[a], v[a | jr]), hi = fmax(v[a], v[a | jr]);
-            v[a] = up ? lo : hi; v[a | jr] = up ? hi : lo;
-          }
-        }
+      if (j >= 32) {                       // only for NR == 2: exchange between the two registers of a lane
+        const bool up = (lane & k) == 0;   // element index of v[0] is `lane` (< 32), k is 64 here: always ascending
+        const double lo = fmin(v[0], v[NR - 1]), hi = fmax(v[0], v[NR - 1]);
+        v[0] = up ? lo : hi; v[NR - 1] = up ? hi : lo;
       } else {
+        const bool lower = (lane & j) == 0;
 #pragma unroll
         for (int a = 0; a < NR; ++a) {
           const double other = __shfl_xor_sync(FULL, v[a], j);
           const bool up = (((a << 5) | lane) & k) == 0;
-          const bool lower = (lane & j) == 0;
-          v[a] = (lower == up) ? fmin(v[a], other) : fmax(v[a], other);
+          const bool take_other = (lower == up) ? (other < v[a]) : (other > v[a]);
+          v[a] = take_other ? other : v[a];
         }
       }
     }
@@ -88,16 +85,14 @@ __device__ double mad_of_sorted(const double* s, int n, double med, int lane) {
   return 0.5 * (dprev + dh);
 }
 
-// index of the first element of s[0..n) that is >= v (lower) / > v (upper)
+// index of the first element of s[0..n) that is >= v (lower) / > v (upper); trip count depends on n only
 __device__ __forceinline__ int bound(const double* s, int n, double v, bool upper) {
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    const double x = s[mid];
-    const bool right = upper ? (x <= v) : (x < v);
-    if (right) lo = mid + 1; else hi = mid;
+  int pos = 0;
+  for (int step = 1 << (31 - __clz(n)); step > 0; step >>= 1) {
+    const int idx = pos + step;
+    if (idx <= n) { const double x = s[idx - 1]; if (upper ? (x <= v) : (x < v)) pos = idx; }
   }
-  return lo;
+  return pos;
 }
 
 struct Sums { double s1, snr; int nsnr; };
@@ -131,8 +126,8 @@ __device__ void band_stats(const double* t, const double* f, const double* e, in
   int b1 = 0, b2 = 0;
   if (sd > 0.0) {
     for (int i = lane; i < n; i += 32) {
-      const double za = fabs(f[i] - mean) / sd;
-      b1 += (za > 1.0); b2 += (za > 2.0);
+      const double ad = fabs(f[i] - mean);
+      b1 += (ad > sd); b2 += (ad > 2.0 * sd);
     }
     b1 = __reduce_add_sync(FULL, b1); b2 = __reduce_add_sync(FULL, b2);
   }
@@ -175,7 +170,7 @@ __device__ void band_stats(const double* t, const double* f, const double* e, in
 }
 
 constexpr int SF_ROW = 160;   // 123-value row + a dump slot for the unknown-filter segment's statistics
-__host__ __device__ inline size_t sf_warp_doubles(int cap) { return 6 * (size_t)cap + SF_ROW; }
+__host__ __device__ inline size_t sf_warp_doubles(int cap) { return 5 * (size_t)cap + SF_ROW; }
 
 __global__ void __launch_bounds__(SF_WARPS_MAX * 32)
 k_stat(const long long* __restrict__ seg_off, const double* __restrict__ gt, const double* __restrict__ gf,
@@ -188,8 +183,8 @@ k_stat(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
   double* sf = st + cap;
   double* se = sf + cap;        // errors during the band phase, time-ordered times afterwards
   double* run = se + cap;       // seven sorted runs, back to back (same offsets as the segments)
-  double* mrg = run + cap;      // merged sorted fluxes; scratch for long bands before that
-  double* tf = mrg + cap;       // time-ordered fluxes
+  double* tf = run + cap;       // time-ordered fluxes; scratch for the sort of long bands before that
+  double* mrg = st;             // merged sorted fluxes: the staged times are dead once the time-ordered copy exists
   for (long long o = (long long)blockIdx.x * nwarps + warp; o < n_obj; o += (long long)gridDim.x * nwarps) {
     const long long* so = seg_off + o * N_SEG;
     const long long base = so[0];
@@ -211,7 +206,7 @@ k_stat(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
         if (b < N_BAND) { if (lane == 0) row[b * N_STAT] = 0.0; if (lane >= 1 && lane < N_STAT) row[b * N_STAT + lane] = qnan(); }
         continue;
       }
-      band_stats(st + lo, sf + lo, se + lo, nb, run + lo, mrg, (b < N_BAND) ? row + b * N_STAT : row + 140, acc, lane);
+      band_stats(st + lo, sf + lo, se + lo, nb, run + lo, tf, (b < N_BAND) ? row + b * N_STAT : row + 140, acc, lane);
       __syncwarp();
     }
     // ---- all rows (statistical.py:186-190)
@@ -221,6 +216,14 @@ k_stat(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
       if (lane >= 1 && lane < N_STAT) ra[lane] = qnan();
     } else {
       const double dn = (double)n;
+      // time order from the stored time rank; the error array is dead by now
+      double* tt = se;
+      if (n <= 256) {
+        for (int i = lane, q = 0; i < n; i += 32, ++q) { tt[trk[q]] = st[i]; tf[trk[q]] = sf[i]; }
+      } else {
+        for (int i = lane; i < n; i += 32) { const int k = gtrank[base + i]; tt[k] = st[i]; tf[k] = sf[i]; }
+      }
+      __syncwarp();
       // merged sorted fluxes: rank of every run element among all runs (stable: earlier runs win ties)
       for (int i = lane; i < n; i += 32) {
         int q = 0;
@@ -233,14 +236,6 @@ k_stat(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
           if (r != q && nr > 0) pos += bound(run + off[r], nr, v, r < q);
         }
         mrg[pos] = v;
-      }
-      // time order from the stored time rank; the error array is dead by now
-      double* tt = se;
-      __syncwarp();
-      if (n <= 256) {
-        for (int i = lane, q = 0; i < n; i += 32, ++q) { tt[trk[q]] = st[i]; tf[trk[q]] = sf[i]; }
-      } else {
-        for (int i = lane; i < n; i += 32) { const int k = gtrank[base + i]; tt[k] = st[i]; tf[k] = sf[i]; }
       }
       __syncwarp();
       const double mean = acc.s1 / dn;
@@ -257,7 +252,7 @@ k_stat(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
       const double sd = (n > 1) ? sqrt(m2 / dn) : 0.0;
       int b1 = 0, b2 = 0;
       if (sd > 0.0) {
-        for (int i = lane; i < n; i += 32) { const double za = fabs(sf[i] - mean) / sd; b1 += (za > 1.0); b2 += (za > 2.0); }
+        for (int i = lane; i < n; i += 32) { const double ad = fabs(sf[i] - mean); b1 += (ad > sd); b2 += (ad > 2.0 * sd); }
         b1 = __reduce_add_sync(FULL, b1); b2 = __reduce_add_sync(FULL, b2);
       }
       const double med = sorted_median(mrg, n);
@@ -303,9 +298,12 @@ k_stat(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
 
 int run_stat(const mlrn_store* s, double* out_dev, cudaStream_t st) {
   if (s->n_obj == 0) return MLRN_OK;
-  const int cap = next_pow2(s->max_obs > 32 ? s->max_obs : 32);
-  int warps = SF_WARPS_MAX;
-  while (warps > 1 && sf_warp_doubles(cap) * sizeof(double) * warps > 110 * 1024) warps >>= 1;
+  // staging capacity per warp: the longest object, and room for the power-of-two padding of the long-band sort
+  int cap = (s->max_obs + 7) & ~7;
+  if (cap < 32) cap = 32;
+  if (s->max_seg > 64 && cap < next_pow2(s->max_seg)) cap = next_pow2(s->max_seg);
+  int warps = 4;
+  while (warps > 1 && sf_warp_doubles(cap) * sizeof(double) * warps > 56 * 1024) warps >>= 1;
   const size_t smem = sf_warp_doubles(cap) * sizeof(double) * warps;
   MLRN_CUDA(cudaFuncSetAttribute(k_stat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
