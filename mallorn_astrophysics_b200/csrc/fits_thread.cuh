@@ -60,16 +60,19 @@ struct BazinJob {
 // decline models on the post-peak suffix of a time-sorted band: x_i = t_i - t_peak, y_i = f_i
 struct PowerModelT {
   const double* t; const double* y; double pt, k;
+  MLRN_FN double fd_row(int i, const double* x, const double* xpd, const double* dx, double* row) const { return generic_fd_row<2>(*this, i, x, xpd, dx, row); }
   MLRN_FN_FORCE double value(int i, const double* p) const { return p[0] * pow(fmax((t[i] - pt) - p[1], 0.1), k); }
   MLRN_FN_FORCE double resid(int i, const double* p) const { return value(i, p) - y[i]; }
 };
 struct ExpModelT {
   const double* t; const double* y; double pt, k;
+  MLRN_FN double fd_row(int i, const double* x, const double* xpd, const double* dx, double* row) const { return generic_fd_row<3>(*this, i, x, xpd, dx, row); }
   MLRN_FN_FORCE double value(int i, const double* p) const { return p[0] * exp(-fmax((t[i] - pt) - p[2], 0.0) / p[1]); }
   MLRN_FN_FORCE double resid(int i, const double* p) const { return value(i, p) - y[i]; }
 };
 struct LinModelT {
   const double* t; const double* y; double pt, k;
+  MLRN_FN double fd_row(int i, const double* x, const double* xpd, const double* dx, double* row) const { return generic_fd_row<3>(*this, i, x, xpd, dx, row); }
   MLRN_FN_FORCE double value(int i, const double* p) const { return p[0] - p[1] * fmax((t[i] - pt) - p[2], 0.0); }
   MLRN_FN_FORCE double resid(int i, const double* p) const { return value(i, p) - y[i]; }
 };

@@ -47,6 +47,9 @@ MLRN_FN_FORCE double pinf() {
 }
 MLRN_FN_FORCE bool is_nan(double x) { return x != x; }
 MLRN_FN_FORCE bool is_finite(double x) { return fabs(x) < pinf(); }
+#ifndef __CUDACC__
+inline double rsqrt(double x) { return 1.0 / sqrt(x); }   // host instantiation only (tests/hostsim)
+#endif
 MLRN_HD int next_pow2(int n) { int p = 1; while (p < n) p <<= 1; return p; }
 
 #ifdef __CUDACC__

@@ -29,9 +29,10 @@ struct SmallFactor {            // R0: upper triangular, column-major r[c*NP + k
       const double b = v[c];
       if (b != 0.0) {
         const double a = r[c * NP + c];
-        const double h = sqrt(a * a + b * b);
-        const double cs = a / h, sn = b / h;
-        r[c * NP + c] = h;
+        const double h2 = a * a + b * b;
+        const double rh = rsqrt(h2);                 // one MUFU + Newton step instead of sqrt and two divisions
+        const double cs = a * rh, sn = b * rh;
+        r[c * NP + c] = h2 * rh;
 #pragma unroll
         for (int k = c + 1; k < NP; ++k) {
           const double rk = r[k * NP + c], vk = v[k];
@@ -47,6 +48,22 @@ struct SmallFactor {            // R0: upper triangular, column-major r[c*NP + k
 };
 
 enum { TRF_RUNNING = 100 };
+
+// forward-difference row of a model without a specialised fd_row: one full evaluation per parameter
+template <int NP, class Model>
+MLRN_FN double generic_fd_row(const Model& mdl, int i, const double* x, const double* xpd, const double* dx, double* row) {
+  const double r0 = mdl.resid(i, x);
+  double xp[NP];
+#pragma unroll
+  for (int k = 0; k < NP; ++k) xp[k] = x[k];
+#pragma unroll
+  for (int c = 0; c < NP; ++c) {
+    xp[c] = xpd[c];
+    row[c] = (mdl.resid(i, xp) - r0) / dx[c];
+    xp[c] = x[c];
+  }
+  return r0;
+}
 
 template <int NP, class Model>
 struct TrfThread {
@@ -102,7 +119,7 @@ struct TrfThread {
 
   // residual + forward-difference Jacobian at x, streamed into F0; g = J^T f
   MLRN_FN bool jacobian_pass() {
-    double xp[NP][NP], dx[NP];
+    double xpd[NP], dx[NP];                 // perturbed value of parameter c, and the exactly representable step
     for (int c = 0; c < NP; ++c) {
       const double sgn = (x[c] >= 0.0) ? 1.0 : -1.0;
       double h = TRF_SQRT_EPS * sgn * fmax(1.0, fabs(x[c]));
@@ -112,17 +129,16 @@ struct TrfThread {
       const bool fitting = fabs(h) <= fmax(lower, upper);
       if (violated && fitting) h = -h;
       if (!fitting) h = (upper >= lower) ? upper : -lower;
-      for (int k = 0; k < NP; ++k) xp[c][k] = x[k];
-      xp[c][c] = x[c] + h;
-      dx[c] = xp[c][c] - x[c];
+      xpd[c] = x[c] + h;
+      dx[c] = xpd[c] - x[c];
     }
     F0.clear();
     bool bad = false;
     for (int i = 0; i < m; ++i) {
-      const double r0 = mdl.resid(i, x);
       double row[NP];
+      const double r0 = mdl.fd_row(i, x, xpd, dx, row);
 #pragma unroll
-      for (int c = 0; c < NP; ++c) { row[c] = (mdl.resid(i, xp[c]) - r0) / dx[c]; bad = bad || !is_finite(row[c]); }
+      for (int c = 0; c < NP; ++c) bad = bad || !is_finite(row[c]);
       F0.add_row(row, r0);
     }
     if (bad) return false;

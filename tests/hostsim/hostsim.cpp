@@ -11,7 +11,6 @@
 #include "shape.cuh"
 #include "tde.cuh"
 #include "physics.cuh"
-#include "fits.cuh"
 #include "gp_host.hpp"
 #include "fits_thread.cuh"
 
@@ -68,34 +67,6 @@ HS_PASS(hs_color, COLOR_COLS, color_row(tm, v, s.sa.data(), s.sb.data(), s.row.d
 HS_PASS(hs_shape, SHAPE_COLS, shape_row(tm, v, s.sa.data(), s.sb.data(), s.row.data()))
 HS_PASS(hs_tde, TDE_COLS, tde_row(tm, v, s.sa.data(), s.sb.data(), s.sc.data(), s.sd.data(), s.row.data()))
 HS_PASS(hs_physics, PHYSICS_COLS, physics_row(tm, v, zz, s.sa.data(), s.sb.data(), s.row.data()))
-
-int hs_bazin(long long n_obj, const long long* seg_off, const double* t, const double* f, const double* e,
-             const unsigned short* rank, double* out, int* status) {
-  HostTeam tm;
-  Scratch s(2 * MAX_OBS);
-  std::vector<double> work(trf_work_doubles<5>(MAX_OBS));
-  for (long long o = 0; o < n_obj; ++o) {
-    ObjView v;
-    stage_object(tm, seg_off, t, f, e, rank, o, s.t.data(), s.f.data(), s.e.data(), s.rank.data(), v);
-    bazin_row(tm, v, s.sa.data(), work.data(), MAX_OBS, s.row.data(), status ? status + o * 12 : nullptr);
-    std::memcpy(out + o * BAZIN_COLS, s.row.data(), sizeof(double) * BAZIN_COLS);
-  }
-  return 0;
-}
-
-int hs_powerlaw(long long n_obj, const long long* seg_off, const double* t, const double* f, const double* e,
-                const unsigned short* rank, double* out, int* status) {
-  HostTeam tm;
-  Scratch s(2 * MAX_OBS);
-  std::vector<double> work(trf_work_doubles<3>(MAX_OBS));
-  for (long long o = 0; o < n_obj; ++o) {
-    ObjView v;
-    stage_object(tm, seg_off, t, f, e, rank, o, s.t.data(), s.f.data(), s.e.data(), s.rank.data(), v);
-    powerlaw_row(tm, v, s.sa.data(), s.sb.data(), work.data(), MAX_OBS, s.row.data(), status ? status + o * 54 : nullptr);
-    std::memcpy(out + o * POWERLAW_COLS, s.row.data(), sizeof(double) * POWERLAW_COLS);
-  }
-  return 0;
-}
 
 // one-thread-per-fit variants (trf_thread.cuh / fits_thread.cuh)
 int hs_bazin_t(long long n_obj, const long long* seg_off, const double* t, const double* f, const double* e,

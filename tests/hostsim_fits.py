@@ -24,7 +24,7 @@ if __name__ == "__main__":
         n_obj = int(g["n_obj"])
         pk = pack_reference(g["obj"], g["band"], g["t"], g["flux"], g["err"], n_obj)
         for m in mods:
-            fn, nc, ns = {"bazin": ("hs_bazin", 52, 6), "powerlaw": ("hs_powerlaw", 27, 27)}[m]
+            fn, nc, ns = {"bazin": ("hs_bazin_t", 52, 6), "powerlaw": ("hs_powerlaw_t", 27, 27)}[m]
             out, st, dt = run(fn, nc, ns, pk, n_obj)
             ref, pres = g[m + "_rows"], g[m + "_present"]
             got = out[pres]

@@ -67,8 +67,8 @@ def test_trf_templates_follow_scipy(golden, hs):
         g = golden[fixture]
         pk, n_obj = _pack(g)
         keep = g["bazin_present"] != (TIE_OBJECT if fixture == "ref_edge" else -1)
-        ob, _ = _run(hs, "hs_bazin", 52, pk, n_obj, status_cols=12)
-        op, _ = _run(hs, "hs_powerlaw", 27, pk, n_obj, status_cols=54)
+        ob, _ = _run(hs, "hs_bazin_t", 52, pk, n_obj, status_cols=12)
+        op, _ = _run(hs, "hs_powerlaw_t", 27, pk, n_obj, status_cols=54)
         cb = classify_bazin(ob[g["bazin_present"]][keep], g["bazin_rows"][keep])
         cp = classify_r2(op[g["powerlaw_present"]][keep], g["powerlaw_rows"][keep])
         for k in tb:
