@@ -19,10 +19,14 @@
 #define MLRN_FN __device__ inline
 #define MLRN_FN_FORCE __device__ __forceinline__
 #define MLRN_HD __host__ __device__ inline
+#define MLRN_ROLL _Pragma("unroll 1")     // keep the NP-sized loops of the solver rolled (code size)
+#define MLRN_NOINLINE __device__ __noinline__     // one copy per kernel: keeps the thread-per-fit kernels inside the i-cache
 #else
 #define MLRN_FN inline
 #define MLRN_FN_FORCE inline
 #define MLRN_HD inline
+#define MLRN_NOINLINE inline
+#define MLRN_ROLL
 #include <algorithm>
 #include <limits>
 #include <utility>

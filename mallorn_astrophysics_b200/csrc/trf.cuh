@@ -42,7 +42,7 @@ MLRN_FN bool in_bounds(const double* x, const double* lb, const double* ub) {
 
 // scipy.optimize._lsq.common.make_strictly_feasible (+ find_active_constraints)
 template <int NP>
-MLRN_FN void make_strictly_feasible(double* x, const double* lb, const double* ub, double rstep) {
+MLRN_NOINLINE void make_strictly_feasible(double* x, const double* lb, const double* ub, double rstep) {
   for (int i = 0; i < NP; ++i) {
     int active = 0;
     if (rstep == 0.0) {
@@ -73,7 +73,7 @@ MLRN_FN void cl_scaling(const double* x, const double* g, const double* lb, cons
 
 // min step to a bound along s, and which variables hit (scipy step_size_to_bound)
 template <int NP>
-MLRN_FN double step_to_bound(const double* x, const double* s, const double* lb, const double* ub, int* hits) {
+MLRN_NOINLINE double step_to_bound(const double* x, const double* s, const double* lb, const double* ub, int* hits) {
   double steps[NP]; double mn = pinf();
   for (int i = 0; i < NP; ++i) {
     steps[i] = pinf();
@@ -87,7 +87,7 @@ MLRN_FN double step_to_bound(const double* x, const double* s, const double* lb,
   return mn;
 }
 
-MLRN_FN void minimize_quadratic_1d(double a, double b, double lo, double hi, double c, double& t_best, double& y_best) {
+MLRN_NOINLINE void minimize_quadratic_1d(double a, double b, double lo, double hi, double c, double& t_best, double& y_best) {
   double t[3] = {lo, hi, 0.0}; int nt = 2;
   if (a != 0.0) { double ex = -0.5 * b / a; if (lo < ex && ex < hi) { t[2] = ex; nt = 3; } }
   t_best = t[0]; y_best = t[0] * (a * t[0] + b) + c;
@@ -97,12 +97,15 @@ MLRN_FN void minimize_quadratic_1d(double a, double b, double lo, double hi, dou
 // One-sided Jacobi SVD of an NP x NP matrix A (column-major a[c*NP + r]); returns singular values
 // s (descending), right vectors V (v[c*NP + r]) and w = U^T b for a given b.
 template <int NP>
-MLRN_FN void small_svd(double* a, const double* b, double* s, double* V, double* w) {
+MLRN_NOINLINE void small_svd(double* a, const double* b, double* s, double* V, double* w) {
   for (int i = 0; i < NP * NP; ++i) V[i] = 0.0;
   for (int i = 0; i < NP; ++i) V[i * NP + i] = 1.0;
+#pragma unroll 1
   for (int sweep = 0; sweep < 40; ++sweep) {
     bool rotated = false;
+#pragma unroll 1
     for (int p = 0; p < NP - 1; ++p)
+#pragma unroll 1
       for (int q = p + 1; q < NP; ++q) {
         double al = 0.0, be = 0.0, ga = 0.0;
         for (int r = 0; r < NP; ++r) { double x = a[p * NP + r], y = a[q * NP + r]; al += x * x; be += y * y; ga += x * y; }
@@ -142,7 +145,7 @@ MLRN_FN void small_svd(double* a, const double* b, double* s, double* V, double*
 
 // scipy solve_lsq_trust_region (More's iteration on the secular equation)
 template <int NP>
-MLRN_FN void solve_lsq_tr(int m, const double* uf, const double* s, const double* V, double Delta, double& alpha, double* p) {
+MLRN_NOINLINE void solve_lsq_tr(int m, const double* uf, const double* s, const double* V, double Delta, double& alpha, double* p) {
   double suf[NP];
   for (int i = 0; i < NP; ++i) suf[i] = s[i] * uf[i];
   bool full_rank = false;

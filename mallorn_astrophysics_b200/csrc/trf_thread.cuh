@@ -23,7 +23,7 @@ struct SmallFactor {            // R0: upper triangular, column-major r[c*NP + k
   double q[NP];
   MLRN_FN void clear() { for (int i = 0; i < NP * NP; ++i) r[i] = 0.0; for (int i = 0; i < NP; ++i) q[i] = 0.0; }
   // fold the row (v, rhs) in; v is destroyed
-  MLRN_FN void add_row(double* v, double rhs) {
+  MLRN_NOINLINE void add_row(double* v, double rhs) {
 #pragma unroll
     for (int c = 0; c < NP; ++c) {
       const double b = v[c];
@@ -77,7 +77,7 @@ struct TrfThread {
   int nfev, status;
   bool need_jac;
 
-  MLRN_FN double residual_cost(const double* xx, bool& finite) const {
+  MLRN_NOINLINE double residual_cost(const double* xx, bool& finite) const {
     double acc = 0.0; bool bad = false;
     for (int i = 0; i < m; ++i) { const double r = mdl.resid(i, xx); acc += r * r; bad = bad || !is_finite(r); }
     finite = !bad;
@@ -85,7 +85,7 @@ struct TrfThread {
   }
 
   // (J_h a) . (J_h b) with J_h = Q R0 D
-  MLRN_FN double jh_dot(const double* a, const double* b) const {
+  MLRN_NOINLINE double jh_dot(const double* a, const double* b) const {
     double acc = 0.0;
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
@@ -96,7 +96,7 @@ struct TrfThread {
     }
     return acc;
   }
-  MLRN_FN double eval_quadratic(const double* s) const {
+  MLRN_NOINLINE double eval_quadratic(const double* s) const {
     double q = jh_dot(s, s);
     for (int c = 0; c < NP; ++c) q += s[c] * diag_h[c] * s[c];
     return 0.5 * q + vdot<NP>(s, g_h);
@@ -118,7 +118,7 @@ struct TrfThread {
   }
 
   // residual + forward-difference Jacobian at x, streamed into F0; g = J^T f
-  MLRN_FN bool jacobian_pass() {
+  MLRN_NOINLINE bool jacobian_pass() {
     double xpd[NP], dx[NP];                 // perturbed value of parameter c, and the exactly representable step
     for (int c = 0; c < NP; ++c) {
       const double sgn = (x[c] >= 0.0) ? 1.0 : -1.0;
