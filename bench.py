@@ -173,7 +173,7 @@ def workload_config(args, objects_per_gpu, modules):
 # ----------------------------------------------------------------------------------------------
 def algorithmic_bytes(n_rows, n_obj):
     """Moment pass, SURVEY.md 8(d) with this build's layout: one read of every observation
-    (t, flux, err float64 + uint16 file rank = 26 B), the 8 segment offsets of the object (int64) and one
+    (t, flux, err float64 + uint16 time rank = 26 B), the 8 segment offsets of the object (int64) and one
     write of the 123-column float64 row."""
     return 26 * n_rows + n_obj * (8 * 8 + 123 * 8)
 
@@ -304,7 +304,7 @@ def run_gpu_arm(args):
         roof = None
         if stat_ms:
             ach = algorithmic_bytes(n_rows, n_obj) / (stat_ms * 1e-3) / 1e9
-            roof = {"kernel": "k_pass<PASS_STAT> (moment pass)", "bound": "hbm", "achieved": ach, "peak": peak,
+            roof = {"kernel": "k_stat (moment pass, stat_fast.cu)", "bound": "hbm", "achieved": ach, "peak": peak,
                     "unit": "GB/s", "frac": ach / peak, "traffic": None,
                     "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s",
                     "algorithmic_bytes_per_launch": algorithmic_bytes(n_rows, n_obj), "ms_per_launch": stat_ms}
@@ -338,7 +338,7 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--objects", type=int, default=1_000_000, help="objects per GPU per step")
