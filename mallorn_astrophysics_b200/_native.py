@@ -11,7 +11,7 @@ import os
 from typing import Optional
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmallorn_b200.so")
+LIB_PATH = os.environ.get("MLRN_LIB") or os.path.join(HERE, "libmallorn_b200.so")   # MLRN_LIB: developer builds (profiling flags)
 
 COLS = {"statistical": 123, "colors": 83, "shape": 65, "tde": 25, "physics": 32,
         "bazin": 52, "powerlaw": 27, "gp2d": 27}

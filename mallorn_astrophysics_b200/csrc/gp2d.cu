@@ -87,19 +87,27 @@ __device__ __forceinline__ KernelPars unpack(const double* p) {
 // over the shared-memory banks, and (r, r+1) pairs with r even stay one aligned double2
 __device__ __forceinline__ int tix(int r, int c) { return c * TB + (r ^ (c & 14)); }
 
+// running product of the pivots as mantissa * 2^exponent (ln|K| is taken once per evaluation, off the critical path)
+struct LogDet {
+  double m; int e;
+  __device__ __forceinline__ void mul(double x) { int ex; m *= frexp(x, &ex); e += ex; m = frexp(m, &ex); e += ex; }
+  __device__ __forceinline__ double value() const { return log(m) + (double)e * 0.6931471805599453; }
+};
+
 // Pivot tile k, one warp.  Lanes 0..15 hold one row of A_kk each and turn it into L = chol(A_kk) (right-
 // looking, the column being eliminated is broadcast by shuffle); lanes 16..31 hold one column of L^-1 each and
 // ride on the SAME broadcasts: forward substitution of column j needs exactly L[c2][c] x_c, the term the
-// Cholesky update multiplies by L[r][c].  Then w = L^-1 b_k.  Results in S.Li / S.LiT / S.w [buf];
-// ln|K| from the product of the pivots.
-__device__ __forceinline__ void pivot_warp(const GpShared& S, int k, int buf, double& quad, double& logdet, int& fail) {
+// Cholesky update multiplies by L[r][c].  The right-hand side b_k is carried as one more value per row lane,
+// so w = L^-1 b_k also falls out of the same loop.  Results in S.Li / S.LiT / S.w [buf].
+__device__ __forceinline__ void pivot_warp(const GpShared& S, int k, int buf, double& quad, LogDet& logdet, int& fail) {
   const int lane = threadIdx.x & 31, r = lane & 15;
   const bool lower = lane < TB;
   const double* A = tile_ptr(S, k, k);
   double val[TB];
 #pragma unroll
   for (int c = 0; c < TB; ++c) val[c] = lower ? A[tix(r, c)] : ((c == r) ? 1.0 : 0.0);
-  double prod = 1.0; bool bad = false;
+  double bw = lower ? S.sb[k * TB + r] : 0.0;      // rhs of this row; becomes w_r at step r
+  double wr = 0.0, prod = 1.0; bool bad = false;
 #pragma unroll
   for (int c = 0; c < TB; ++c) {
     const double piv = __shfl_sync(FULLMASK, val[c], c);
@@ -108,23 +116,22 @@ __device__ __forceinline__ void pivot_warp(const GpShared& S, int k, int buf, do
     prod *= piv;
     const double mult = val[c] * ri;       // L[r][c] on the lower lanes, (L^-1)[c][j] on the upper lanes
     val[c] = mult;
+    const double wc = __shfl_sync(FULLMASK, bw, c) * ri;       // w_c = (b_c - sum_{m<c} L[c][m] w_m) / L[c][c]
+    if (lane == c) wr = wc;
+    bw -= mult * wc;                       // rows below c (other lanes: harmless)
 #pragma unroll
     for (int c2 = c + 1; c2 < TB; ++c2) val[c2] -= mult * __shfl_sync(FULLMASK, mult, c2);
   }
   if (!lower) {
 #pragma unroll
     for (int q = 0; q < TB; ++q) { S.Li[buf * TT + q * TB + r] = val[q]; S.LiT[buf * VT + r * VLD + q] = val[q]; }   // Li[q][j], j = r
+  } else {
+    S.w[buf * TB + r] = wr;
   }
-  __syncwarp();
-  double wq = 0.0;
-  if (lower) {
-    double s = 0.0;
-    for (int c = 0; c <= r; ++c) s += S.LiT[buf * VT + c * VLD + r] * S.sb[k * TB + c];       // Li[r][c]
-    S.w[buf * TB + r] = s; wq = s * s;
-  }
+  double wq = lower ? wr * wr : 0.0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) wq += __shfl_xor_sync(FULLMASK, wq, o);
-  quad += wq; logdet += log(prod);
+  quad += wq; logdet.mul(prod);
   if (bad || !(prod == prod)) fail = 1;
   __syncwarp();
 }
@@ -223,9 +230,19 @@ __device__ __forceinline__ void tile_finalise(double* __restrict__ Tl, bool tran
 // -ln L and its gradient at p.  Leaves alpha in S.sb[0..n).  Result broadcast to every thread.
 // cache: per-CTA global (L2-resident) scratch [2][nt * 256] holding s and exp(-s) of every matrix element
 // between the build and the gradient contraction.
+#ifdef GP_PHASE_TIMING
+__device__ unsigned long long g_gp_phase[8];     // developer build only: cycles per phase summed over CTA 0's evaluations
+#define GP_TICK(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd(&g_gp_phase[slot], (unsigned long long)(now_ - t_mark_)); t_mark_ = now_; } } while (0)
+#else
+#define GP_TICK(slot) do { } while (0)
+#endif
+
 __device__ __forceinline__ void gp_eval(const GpShared& S, double* __restrict__ cache, int n, int T, int T_cap,
                                         const double* p, double& f, double* grad) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef GP_PHASE_TIMING
+  long long t_mark_ = clock64();
+#endif
   const KernelPars kp = unpack(p);
   const int nt = n_tiles(T);
   double* cache_s = cache;
@@ -247,11 +264,13 @@ __device__ __forceinline__ void gp_eval(const GpShared& S, double* __restrict__ 
     S.tiles[tl * TT + tix(r, c)] = v;
   }
   for (int i = tid; i < T * TB; i += GP_THREADS) S.sb[i] = (i < n) ? S.sy[i] - kp.mean : 0.0;
-  double quad = 0.0, logdet = 0.0; int fail = 0;      // accumulated by warp 0 (uniform across its lanes)
+  double quad = 0.0; LogDet logdet{1.0, 0}; int fail = 0;     // accumulated by warp 0 (uniform across its lanes)
   __syncthreads();
+  GP_TICK(0);
   // ---- (b) tile sweep with look-ahead: warp 0 owns the critical path (next pivot tile), warps 1.. the bulk
   if (warp == 0) pivot_warp(S, 0, 0, quad, logdet, fail);
   __syncthreads();
+  GP_TICK(1);
   for (int k = 0; k < T; ++k) {
     const int cur = k & 1, nxt = cur ^ 1;
     const double* Li = S.Li + cur * TT;
@@ -264,18 +283,24 @@ __device__ __forceinline__ void gp_eval(const GpShared& S, double* __restrict__ 
       else tile_scale(S.vbuf + i * VT, tile_ptr(S, k, i), true, LiT);
     }
     __syncthreads();
+    GP_TICK(2);
     if (warp == 0) {
       if (k + 1 < T) {                                // finish row k+1 of this step first, then factor it
         const double* V = S.vbuf + (k + 1) * VT;
         tile_update(tile_ptr(S, k + 1, k + 1), V, V);
-        if (lane < TB) {
+        {                                             // b_{k+1} -= V_{k+1} w_k, the 16-term sums split over the two half-warps
+          const int rr = lane & 15, m0 = (lane >> 4) * 8;
           double s = 0.0;
-          for (int m = 0; m < TB; ++m) s += V[m * VLD + lane] * wv[m];
-          S.sb[(k + 1) * TB + lane] -= s;
+#pragma unroll
+          for (int m = 0; m < 8; ++m) s += V[(m0 + m) * VLD + rr] * wv[m0 + m];
+          s += __shfl_xor_sync(FULLMASK, s, 16);
+          if (lane < TB) S.sb[(k + 1) * TB + lane] -= s;
         }
         __syncwarp();
+        GP_TICK(3);
         pivot_warp(S, k + 1, nxt, quad, logdet, fail);
       }
+      GP_TICK(6);
     } else {
       // warp tasks: rank-16 updates of every tile outside row/column k ((k+1, k+1) belongs to warp 0),
       // then column k <- V_i Li.  Disjoint tiles, so no ordering between them.
@@ -303,6 +328,11 @@ __device__ __forceinline__ void gp_eval(const GpShared& S, double* __restrict__ 
         for (int m = (r > c ? r : c); m < TB; ++m) s += Li[m * TB + r] * Li[m * TB + c];
         tile_ptr(S, k, k)[tix(r, c)] = -s;
       }
+      if (t2 < TB) {                                  // b_k <- Li^T w (nobody reads b_k or w_k any more in this step)
+        double s = 0.0;
+        for (int m = t2; m < TB; ++m) s += Li[m * TB + t2] * wv[m];
+        S.sb[k * TB + t2] = s;
+      }
       for (int i = t2; i < T * TB; i += nth) {
         const int ti = i >> 4, r = i & 15;
         if (ti != k && ti != k + 1) {
@@ -314,11 +344,7 @@ __device__ __forceinline__ void gp_eval(const GpShared& S, double* __restrict__ 
       }
     }
     __syncthreads();
-    if (tid < TB) {                                   // b_k <- Li^T w  (after every reader of the old b_k / w)
-      double s = 0.0;
-      for (int m = tid; m < TB; ++m) s += Li[m * TB + tid] * wv[m];
-      S.sb[k * TB + tid] = s;
-    }
+    GP_TICK(4);
   }
   __syncthreads();
   // ---- (c) gradient contraction: 1/2 sum (alpha_i alpha_j - Kinv_ij) dK_ij ; tiles hold -Kinv
@@ -338,7 +364,8 @@ __device__ __forceinline__ void gp_eval(const GpShared& S, double* __restrict__ 
       acc[1] += Aij * kp.amp * (1.0 + s) * ex; acc[2] += Aij * dk * a0; acc[3] += Aij * dk * a1;
     }
   }
-  if (tid == 0) { S.bc[0] = quad; S.bc[1] = logdet; S.bc[2] = (double)fail; }
+  GP_TICK(5);
+  if (tid == 0) { S.bc[0] = quad; S.bc[1] = logdet.value(); S.bc[2] = (double)fail; }
   block_sum4(S, acc);                                 // contains the barriers that publish bc[]
   const double ll = -0.5 * S.bc[0] - 0.5 * S.bc[1] - 0.5 * (double)n * LOG_2PI;
   if (S.bc[2] != 0.0 || !is_finite(ll)) {             // multiband_gp.py:141-154: 1e25 and a zero gradient
@@ -548,6 +575,14 @@ k_gp2d(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
 }
 
 }  // namespace
+
+#ifdef GP_PHASE_TIMING
+extern "C" void mlrn_gp_phase_cycles(unsigned long long* out8, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out8, g_gp_phase, sizeof(unsigned long long) * 8);
+  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_gp_phase, z, sizeof(z)); }
+}
+#endif
 
 int run_gp2d(const mlrn_store* s, double* out_dev, int* status_dev, cudaStream_t st) {
   if (s->n_obj == 0) return MLRN_OK;
