@@ -17,7 +17,7 @@ with LightCurveStore.from_table(table) as s:
     L.mlrn_gp_phase_cycles(buf, 1)
     s.features("gp2d", status=st)
     L.mlrn_gp_phase_cycles(buf, 0)
-names = ["build", "pivot0", "phaseA(scale)+sync", "warp0: update+pivot", "phaseB tail wait (sync)", "gradient", "-", "-"]
+names = ["build", "pivot0", "phaseA(scale)+sync", "warp0: tile update + b", "phaseB tail wait (sync)", "gradient", "warp0: pivot", "-"]
 tot = sum(buf)
 for k, nm in enumerate(names):
     if buf[k]: print(f"{nm:28s} {buf[k]:14d} cycles  {100*buf[k]/tot:5.1f}%")
