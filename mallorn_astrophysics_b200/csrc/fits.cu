@@ -13,9 +13,9 @@ namespace {
 // evaluation per trip, and a lane whose fit ends takes the next (object, band[, model]) from the
 // ticket counter, so the 100x spread in iteration counts does not idle the warp.
 // ------------------------------------------------------------------------------------------------
-constexpr int FIT_THREADS = 128;
+constexpr int FIT_THREADS = 512;          // 8 warps that start every trip together (see the barrier in the loops)
 
-__global__ void __launch_bounds__(FIT_THREADS, 4)
+__global__ void __launch_bounds__(FIT_THREADS, 1)
 k_bazin_thread(const long long* __restrict__ seg_off, const double* __restrict__ gt, const double* __restrict__ gf,
                const double* __restrict__ ge, int n_obj, unsigned long long* __restrict__ ticket,
                double* __restrict__ out, int* __restrict__ status) {
@@ -37,7 +37,7 @@ k_bazin_thread(const long long* __restrict__ seg_off, const double* __restrict__
         if (status) { status[fit * 2] = code; status[fit * 2 + 1] = 0; }
       }
     }
-    if (!__any_sync(0xffffffffu, active || !exhausted)) break;
+    if (!__syncthreads_or(active || !exhausted)) break;      // also lines the warps up: they fetch the same code
     if (active) {
       const int rc = job.step();
       if (rc != TRF_RUNNING) {
@@ -67,7 +67,7 @@ __global__ void k_bazin_tail(int n_obj, double* __restrict__ out) {
 
 // KIND 0: the seven fixed-index power laws (21 fits per object); 1: exponential; 2: linear (3 per object each)
 template <int KIND>
-__global__ void __launch_bounds__(FIT_THREADS, 4)
+__global__ void __launch_bounds__(FIT_THREADS, 1)
 k_decline_thread(const long long* __restrict__ seg_off, const double* __restrict__ gt, const double* __restrict__ gf,
                  int n_obj, unsigned long long* __restrict__ ticket, double* __restrict__ out, int* __restrict__ status) {
   constexpr int PER_BAND = (KIND == 0) ? 7 : 1;
@@ -97,7 +97,7 @@ k_decline_thread(const long long* __restrict__ seg_off, const double* __restrict
         if (status) { status[s * 2] = code; status[s * 2 + 1] = 0; }
       }
     }
-    if (!__any_sync(0xffffffffu, active || !exhausted)) break;
+    if (!__syncthreads_or(active || !exhausted)) break;
     if (active) {
       const int rc = job.step();
       if (rc != TRF_RUNNING) {
