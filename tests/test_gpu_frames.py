@@ -1,0 +1,90 @@
+"""The drop-in boundary itself: the reference's function names, signatures and DataFrame schema
+(SURVEY.md section 8b), served from the GPU through ctypes -> libmallorn_b200.so."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BANDS = np.array(["u", "g", "r", "i", "z", "y", "X"], dtype=object)
+
+
+def _frames(g):
+    import pandas as pd
+    n_obj = int(g["n_obj"])
+    ids = np.array([f"Obj_{k:04d}_name" for k in range(n_obj)], dtype=object)
+    lc = pd.DataFrame({"object_id": ids[g["obj"]], "Time (MJD)": g["t"], "Flux": g["flux"], "Flux_err": g["err"],
+                       "Filter": BANDS[np.minimum(g["band"], 6)]})
+    meta = pd.DataFrame({"object_id": ids, "Z": g["z"], "EBV": g["ebv"]})
+    return lc, meta, ids
+
+
+@pytest.fixture(scope="module")
+def features_pkg():
+    """`import features` exactly as a reference driver would after the one-line sys.path switch."""
+    sys.path.insert(0, os.path.join(ROOT, "mallorn_astrophysics_b200"))
+    try:
+        for name in [m for m in sys.modules if m == "features" or m.startswith("features.")]:
+            del sys.modules[name]
+        yield importlib.import_module("features")
+    finally:
+        sys.path.remove(os.path.join(ROOT, "mallorn_astrophysics_b200"))
+
+
+CASES = [("statistical", "features.statistical", "extract_statistical_features", False),
+         ("colors", "features.colors", "extract_color_features", False),
+         ("shape", "features.lightcurve_shape", "extract_shape_features", False),
+         ("tde", "features.tde_physics", "extract_tde_physics_features", False),
+         ("physics", "features.physics_based", "extract_physics_features", True),
+         ("bazin", "features.bazin_fitting", "extract_bazin_features", False),
+         ("gp2d", "features.multiband_gp", "extract_multiband_gp_features", True),
+         ("powerlaw", "features.powerlaw", "extract_powerlaw_features", False)]
+
+
+@pytest.mark.parametrize("module,modname,fn,needs_meta", CASES)
+def test_extractors_keep_the_reference_schema(golden, features_pkg, module, modname, fn, needs_meta):
+    from mallorn_astrophysics_b200 import schema
+    g = golden["ref_edge"]                                  # object 20 has no rows: must be omitted
+    lc, meta, ids = _frames(g)
+    lc_before = lc.copy()
+    extract = getattr(importlib.import_module(modname), fn)
+    request = list(ids[::-1])                               # rows come back in REQUEST order
+    df = extract(lc, meta, request) if needs_meta else extract(lc, request)
+    cols = schema.MODULE_COLUMNS[module]
+    if module in ("statistical", "powerlaw"):
+        assert list(df.columns) == ["object_id"] + cols     # statistical.py:166, train_v55_powerlaw.py:197
+    else:
+        assert list(df.columns) == cols + ["object_id"]     # e.g. colors.py:377
+    present = [i for i in request if i != ids[20]]
+    assert list(df["object_id"]) == present                 # absent ids are omitted (statistical.py:163-165)
+    assert lc.equals(lc_before)                             # inputs are not mutated
+    if module == "statistical":
+        assert all(str(df[c].dtype).startswith("int") for c in schema.STAT_INT_COLUMNS)
+    if module in ("statistical", "colors", "shape", "tde", "physics"):
+        ref_rows = g[f"{module}_rows"]
+        ref_present = g[f"{module}_present"]
+        order = [int(np.flatnonzero(ids == i)[0]) for i in df["object_id"]]
+        want = np.array([ref_rows[np.flatnonzero(ref_present == k)[0]] for k in order])
+        got = df[cols].to_numpy(dtype=float)
+        keep = np.array(order) != 15                        # the tie object (unstable sort upstream)
+        assert np.array_equal(np.isnan(got[keep]), np.isnan(want[keep]))
+        ok = ~np.isnan(want) & keep[:, None]
+        np.testing.assert_allclose(got[ok], want[ok], rtol=1e-5, atol=1e-9)
+
+
+def test_default_object_ids_and_metadata_merge(golden, features_pkg):
+    g = golden["ref_sparse"]
+    lc, meta, ids = _frames(g)
+    st = importlib.import_module("features.statistical")
+    df = st.extract_statistical_features(lc)                # object_ids=None -> unique() order of the light curves
+    assert list(df["object_id"]) == list(lc["object_id"].unique())
+    full = st.add_metadata_features(df, meta)               # statistical.py:229-253
+    assert list(full.columns[-4:]) == ["Z", "EBV", "luminosity_distance", "time_dilation"]
+    z = meta.set_index("object_id").loc[full["object_id"], "Z"].to_numpy()
+    np.testing.assert_allclose(full["luminosity_distance"], 4280 * z)
+    np.testing.assert_allclose(full["time_dilation"], 1 + z)
+    assert importlib.import_module("features").extract_statistical_features is st.extract_statistical_features
