@@ -12,8 +12,7 @@ from typing import Optional, Sequence
 
 import numpy as np
 
-from .. import schema
-from ..store import LightCurveStore
+from ._compat import LightCurveStore, schema
 
 
 def _request_index(ids, object_ids):

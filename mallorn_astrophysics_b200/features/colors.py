@@ -10,7 +10,8 @@ from typing import List, Optional
 
 import pandas as pd
 
-from ..schema import LSST_BANDS as _BANDS
+from ._compat import schema as _schema
+_BANDS = _schema.LSST_BANDS
 from ._frames import run_frame_module
 
 LSST_BANDS = list(_BANDS)

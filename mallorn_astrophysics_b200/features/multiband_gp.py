@@ -12,7 +12,8 @@ from typing import List, Optional
 
 import pandas as pd
 
-from ..schema import BAND_WAVELENGTHS_A as BAND_WAVELENGTHS  # noqa: F401  (multiband_gp.py:26-29, Angstrom)
+from ._compat import schema as _schema
+BAND_WAVELENGTHS = _schema.BAND_WAVELENGTHS_A          # multiband_gp.py:26-29, Angstrom
 from ._frames import run_frame_module
 
 

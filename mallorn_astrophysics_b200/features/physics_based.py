@@ -10,7 +10,9 @@ from typing import List, Optional
 
 import pandas as pd
 
-from ..schema import LSST_BANDS as _BANDS, BAND_WAVELENGTHS_A as BAND_WAVELENGTHS_A  # noqa: F401
+from ._compat import schema as _schema
+_BANDS = _schema.LSST_BANDS
+BAND_WAVELENGTHS_A = _schema.BAND_WAVELENGTHS_A
 from ._frames import run_frame_module
 
 LSST_BANDS = list(_BANDS)

@@ -6,9 +6,11 @@ HistGradientBoostingClassifier with the same protocol -- 5-fold stratified CV, T
 threshold on the out-of-fold probabilities -- run on the merged 434-column table of a labelled synthetic set.
 North star: |F1_gpu - F1_cpu| <= 0.005.   Usage (GPU box):  python tests/gpu_downstream_f1.py [n_objects]
 """
+import os
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ[_v] = "1"          # one thread per worker process: the parallelism is across processes
 import json
 import multiprocessing as mp
-import os
 import sys
 import time
 import warnings
@@ -37,22 +39,26 @@ def _cpu_chunk(args):
     return lo, np.concatenate(out, axis=1)
 
 
-def oof_f1(X, y, seed=0):
-    os.environ.setdefault("OMP_NUM_THREADS", str(min(16, os.cpu_count() or 1)))
+def _fit_fold(args):
     from sklearn.ensemble import HistGradientBoostingClassifier
+    X, y, tr, va, seed = args
+    clf = HistGradientBoostingClassifier(max_iter=60, learning_rate=0.1, max_depth=5, random_state=seed,
+                                         class_weight="balanced")
+    clf.fit(X[tr], y[tr])
+    return va, clf.predict_proba(X[va])[:, 1]
+
+
+def oof_f1(pool, X, y, seed=0):
     from sklearn.model_selection import StratifiedKFold
+    folds = list(StratifiedKFold(5, shuffle=True, random_state=seed).split(X, y))
     oof = np.zeros(len(y))
-    for tr, va in StratifiedKFold(5, shuffle=True, random_state=seed).split(X, y):
-        clf = HistGradientBoostingClassifier(max_iter=60, learning_rate=0.1, max_depth=5, random_state=seed,
-                                             class_weight="balanced")
-        clf.fit(X[tr], y[tr])
-        oof[va] = clf.predict_proba(X[va])[:, 1]
+    for va, p in pool.map(_fit_fold, [(X, y, tr, va, seed) for tr, va in folds]):
+        oof[va] = p
     best = 0.0
     for thr in np.linspace(0.05, 0.95, 91):
         pred = oof >= thr
         tp = np.sum(pred & (y == 1)); fp = np.sum(pred & (y == 0)); fn = np.sum(~pred & (y == 1))
-        f1 = 2 * tp / max(2 * tp + fp + fn, 1)
-        best = max(best, f1)
+        best = max(best, 2 * tp / max(2 * tp + fp + fn, 1))
     return best
 
 
@@ -68,8 +74,8 @@ def main():
     per = max(1, n // (cores * 4))
     jobs = [(cols, lo, min(lo + per, n)) for lo in range(0, n, per)]
     t0 = time.time()
-    with mp.get_context("fork").Pool(cores) as pool:
-        parts = dict(pool.map(_cpu_chunk, jobs))
+    pool = mp.get_context("fork").Pool(cores)          # forked before this process touches CUDA
+    parts = dict(pool.map(_cpu_chunk, jobs))
     Xc = np.concatenate([parts[lo] for lo in sorted(parts)], axis=0)
     t_cpu = time.time() - t0
     print(f"cpu oracle: {t_cpu:.1f} s on {cores} processes", file=sys.stderr, flush=True)
@@ -82,13 +88,14 @@ def main():
            "cpu_cores": cores, "seeds": {}}
     for seed in (0, 1):
         t0 = time.time()
-        fg, fc = oof_f1(Xg, y, seed), oof_f1(Xc, y, seed)
+        fg, fc = oof_f1(pool, Xg, y, seed), oof_f1(pool, Xc, y, seed)
         print(f"seed {seed}: f1 gpu {fg:.4f} cpu {fc:.4f} ({time.time() - t0:.1f} s)", file=sys.stderr, flush=True)
         res["seeds"][seed] = {"f1_gpu": fg, "f1_cpu": fc, "delta": fg - fc}
     d = [v["delta"] for v in res["seeds"].values()]
     res["mean_abs_delta"] = float(np.mean(np.abs(d)))
     res["max_abs_delta"] = float(np.max(np.abs(d)))
     res["classifier"] = "sklearn HistGradientBoostingClassifier (xgboost is not installed in this image)"
+    pool.close()
     print(json.dumps(res))
 
 

@@ -53,3 +53,22 @@ def test_schema_matches_header(native):
                        ("physics", "PHYSICS"), ("bazin", "BAZIN"), ("powerlaw", "POWERLAW"), ("gp2d", "GP2D")):
         n = int(re.search(rf"#define MLRN_{macro}_COLS (\d+)", hdr).group(1))
         assert n == len(schema.MODULE_COLUMNS[mod]) == native.COLS[mod]
+
+
+def test_features_package_imports_under_both_names():
+    """the reference's drivers import `features.*` after one sys.path line; the same modules are
+    also importable as mallorn_astrophysics_b200.features.  (Import only -- no compute without a GPU.)"""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); "
+            "from features.statistical import extract_statistical_features, add_metadata_features, LSST_BANDS; "
+            "from features.colors import extract_color_features; from features.lightcurve_shape import extract_shape_features; "
+            "from features.physics_based import extract_physics_features; from features.tde_physics import extract_tde_physics_features; "
+            "from features.bazin_fitting import extract_bazin_features, bazin_function; "
+            "from features.multiband_gp import extract_multiband_gp_features; from features.powerlaw import extract_powerlaw_features; "
+            "import features; assert features.extract_statistical_features is extract_statistical_features; "
+            "assert LSST_BANDS == list('ugrizy'); print('ok')") % os.path.join(ROOT, "mallorn_astrophysics_b200")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr
+    import mallorn_astrophysics_b200.features as f2
+    assert callable(f2.extract_color_features)
