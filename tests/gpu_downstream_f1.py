@@ -84,7 +84,13 @@ def main():
         Xg = np.concatenate([s.features(m, z=table.z if m == "physics" else None) for m in MODULES], axis=1)
     t_gpu = time.time() - t0
     print(f"gpu: {t_gpu:.1f} s", file=sys.stderr, flush=True)
-    res = {"objects": n, "positives": int(y.sum()), "columns": int(Xg.shape[1]), "gpu_seconds": t_gpu, "cpu_seconds": t_cpu,
+    # the GBDT stand-in cannot bin columns that are entirely NaN / constant, nor infinities: clean BOTH tables the same way
+    Xg = np.where(np.isfinite(Xg), Xg, np.nan); Xc = np.where(np.isfinite(Xc), Xc, np.nan)
+    usable = np.array([min((~np.isnan(Xc[:, j])).sum(), (~np.isnan(Xg[:, j])).sum()) >= 0.05 * n
+                       and (np.unique(Xc[~np.isnan(Xc[:, j]), j]).size > 1) and (np.unique(Xg[~np.isnan(Xg[:, j]), j]).size > 1)
+                       for j in range(Xc.shape[1])])
+    Xg, Xc = Xg[:, usable], Xc[:, usable]
+    res = {"objects": n, "positives": int(y.sum()), "columns_used": int(Xg.shape[1]), "gpu_seconds": t_gpu, "cpu_seconds": t_cpu,
            "cpu_cores": cores, "seeds": {}}
     for seed in (0, 1):
         t0 = time.time()
