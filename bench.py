@@ -41,6 +41,9 @@ MODULES = ("statistical", "colors", "shape", "tde", "physics", "bazin", "powerla
 METRIC = "light curves/sec for the 222-feature set (full 434-column module table)"
 UNIT = "objects/s"
 SEED = 20260118 + 3            # seed = 20260118 + config index (C4)
+# DRAM traffic of the moment pass from `ncu --set full` (profiles/r01_stat_v2_full.txt: 793.78 MB read + 184.05 MB
+# written for 200,000 objects of this generator) -- 0.99x the algorithmic bytes, i.e. no re-reads
+NCU_STAT_DRAM_BYTES_PER_OBJECT = (793.778688e6 + 184.050432e6) / 200_000
 
 
 # ----------------------------------------------------------------------------------------------
@@ -305,7 +308,9 @@ def run_gpu_arm(args):
         if stat_ms:
             ach = algorithmic_bytes(n_rows, n_obj) / (stat_ms * 1e-3) / 1e9
             roof = {"kernel": "k_stat (moment pass, stat_fast.cu)", "bound": "hbm", "achieved": ach, "peak": peak,
-                    "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "unit": "GB/s", "frac": ach / peak,
+                    "traffic": NCU_STAT_DRAM_BYTES_PER_OBJECT * n_obj,
+                    "traffic_source": "ncu --set full capture at 200k objects (profiles/r01_stat_v2_full.txt), scaled per object",
                     "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s",
                     "algorithmic_bytes_per_launch": algorithmic_bytes(n_rows, n_obj), "ms_per_launch": stat_ms}
         cpu = None
