@@ -231,7 +231,7 @@ __device__ __forceinline__ void tile_finalise(double* __restrict__ Tl, bool tran
 // cache: per-CTA global (L2-resident) scratch [2][nt * 256] holding s and exp(-s) of every matrix element
 // between the build and the gradient contraction.
 #ifdef GP_PHASE_TIMING
-__device__ unsigned long long g_gp_phase[8];     // developer build only: cycles per phase summed over CTA 0's evaluations
+__device__ unsigned long long g_gp_phase[12];     // developer build only: cycles per phase summed over CTA 0's evaluations
 #define GP_TICK(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd(&g_gp_phase[slot], (unsigned long long)(now_ - t_mark_)); t_mark_ = now_; } } while (0)
 #else
 #define GP_TICK(slot) do { } while (0)
@@ -313,7 +313,13 @@ __device__ __forceinline__ void gp_eval(const GpShared& S, double* __restrict__ 
           const int jj = task - ii * (ii + 1) / 2;
           const int i = ii + (ii >= k), j = jj + (jj >= k);
           if (i == k + 1 && j == k + 1) continue;
+#ifdef GP_PHASE_TIMING
+          const long long tu0_ = clock64();
+#endif
           tile_update(tile_ptr(S, i, j), S.vbuf + i * VT, S.vbuf + j * VT);
+#ifdef GP_PHASE_TIMING
+          if (blockIdx.x == 0 && tid == 32) { atomicAdd(&g_gp_phase[8], (unsigned long long)(clock64() - tu0_)); atomicAdd(&g_gp_phase[9], 1ULL); }
+#endif
         } else {
           const int q = task - nupd, i = q + (q >= k);
           if (i > k) tile_finalise(tile_ptr(S, i, k), false, S.vbuf + i * VT, Li);
@@ -579,8 +585,8 @@ k_gp2d(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
 #ifdef GP_PHASE_TIMING
 extern "C" void mlrn_gp_phase_cycles(unsigned long long* out8, int reset) {
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out8, g_gp_phase, sizeof(unsigned long long) * 8);
-  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_gp_phase, z, sizeof(z)); }
+  cudaMemcpyFromSymbol(out8, g_gp_phase, sizeof(unsigned long long) * 12);
+  if (reset) { unsigned long long z[12] = {0}; cudaMemcpyToSymbol(g_gp_phase, z, sizeof(z)); }
 }
 #endif
 

@@ -1,5 +1,5 @@
-// passes.cu -- warp-per-object feature passes over the packed store (K2 moment pass, K3 scalar
-// passes).  One warp stages one object's observations into its shared-memory slice with
+// passes.cu -- warp-per-object K3 scalar feature passes over the packed store (the K2 moment pass is
+// stat_fast.cu).  One warp stages one object's observations into its shared-memory slice with
 // coalesced loads, computes the module's row there, and writes the row back coalesced.
 // Grid = a multiple of the SM count; warps stride over objects.
 #include <cuda_runtime.h>
@@ -20,7 +20,6 @@ constexpr int ROW_CAP = 128;      // >= widest row (123)
 enum PassId { PASS_STAT = 0, PASS_COLOR, PASS_SHAPE, PASS_TDE, PASS_PHYSICS };
 
 template <int PASS> struct PassTraits;
-template <> struct PassTraits<PASS_STAT> { static constexpr int cols = STAT_COLS; static constexpr int scratch = 2; };
 template <> struct PassTraits<PASS_COLOR> { static constexpr int cols = COLOR_COLS; static constexpr int scratch = 2; };
 template <> struct PassTraits<PASS_SHAPE> { static constexpr int cols = SHAPE_COLS; static constexpr int scratch = 2; };
 template <> struct PassTraits<PASS_TDE> { static constexpr int cols = TDE_COLS; static constexpr int scratch = 4; };
@@ -51,7 +50,6 @@ k_pass(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
   for (long long o = (long long)blockIdx.x * PASS_WARPS + warp; o < n_obj; o += (long long)gridDim.x * PASS_WARPS) {
     ObjView v;
     stage_object(tm, seg_off, gt, gf, ge, grank, o, st, sf, se, srank, v);
-    if (PASS == PASS_STAT) stat_row(tm, v, scr, scr + np, row);
     if (PASS == PASS_COLOR) color_row(tm, v, scr, scr + np, row);
     if (PASS == PASS_SHAPE) shape_row(tm, v, scr, scr + np, row);
     if (PASS == PASS_TDE) tde_row(tm, v, scr, scr + np, scr + 2 * np, scr + 3 * np, row);
@@ -83,8 +81,6 @@ int launch_pass(const mlrn_store* s, const double* z, double* out, cudaStream_t 
 
 }  // namespace
 
-// the moment pass proper lives in stat_fast.cu; this generic instantiation is kept as a cross-check
-int run_stat_generic(const mlrn_store* s, double* out_dev, cudaStream_t st) { return launch_pass<PASS_STAT>(s, nullptr, out_dev, st); }
 int run_color(const mlrn_store* s, double* out_dev, cudaStream_t st) { return launch_pass<PASS_COLOR>(s, nullptr, out_dev, st); }
 int run_shape(const mlrn_store* s, double* out_dev, cudaStream_t st) { return launch_pass<PASS_SHAPE>(s, nullptr, out_dev, st); }
 int run_tde(const mlrn_store* s, double* out_dev, cudaStream_t st) { return launch_pass<PASS_TDE>(s, nullptr, out_dev, st); }
