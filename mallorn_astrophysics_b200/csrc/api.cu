@@ -108,6 +108,20 @@ int mlrn_store_create(int device, int64_t n_rows, int32_t n_obj, const int32_t* 
   if (device < 0 || device >= ndev) { set_error("device index out of range"); return MLRN_EINVAL; }
   DevGuard g(device);
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    // Temporaries (input staging, per-pass output staging, pack scratch) are stream-ordered allocations; keep the
+    // pool's memory cached across synchronisation points instead of returning it to the driver after every call.
+    static std::atomic<unsigned> pool_ready{0};
+    if (device < 32 && !(pool_ready.load() & (1u << device))) {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = ~0ULL;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      cudaGetLastError();
+      pool_ready.fetch_or(1u << device);
+    }
+  }
   mlrn_store* s = new (std::nothrow) mlrn_store();
   if (!s) { set_error("out of host memory"); return MLRN_EINVAL; }
   s->device = device; s->n_obj = n_obj;
