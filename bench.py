@@ -138,7 +138,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_step = args.cpu_objects or 16 * cores
+    per_step = args.cpu_objects or 32 * cores
     cols = host_sample(per_step)
     modules = list(MODULES)
     for _ in range(args.warmup):
@@ -316,7 +316,7 @@ def run_gpu_arm(args):
         cpu = None
         if not args.no_cpu:
             cores = os.cpu_count() or 1
-            n_cpu = args.cpu_objects or 8 * cores
+            n_cpu = args.cpu_objects or 48 * cores
             sample_cols = host_sample(n_cpu)
             rate, secs = cpu_rate(sample_cols, n_cpu, modules, cores)
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",

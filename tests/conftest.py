@@ -16,4 +16,4 @@ def pytest_configure(config):
 def golden():
     import numpy as np
     here = os.path.join(ROOT, "tests", "golden")
-    return {n: np.load(os.path.join(here, f"{n}.npz")) for n in ("ref_sparse", "ref_dense", "ref_edge")}
+    return {n: np.load(os.path.join(here, f"{n}.npz")) for n in ("ref_sparse", "ref_dense", "ref_edge", "ref_c1_256")}

