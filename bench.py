@@ -210,6 +210,7 @@ def run_gpu_arm(args):
     width = sum(_native.COLS[m] for m in modules)
     table = torch.empty((n_obj, width), dtype=torch.float64, device=dev)
     gathered = torch.empty((world * n_obj, width), dtype=torch.float64, device=dev) if world > 1 else None
+    gp_status = torch.zeros((n_obj, 4), dtype=torch.int32, device=dev) if "gp2d" in modules else None
     flush = None
     if n_rows * 25 < 2 * 126e6:
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -227,7 +228,8 @@ def run_gpu_arm(args):
         e = ev(); e.record(stream); marks.append(("pack", e))
         c0 = 0
         for m in modules:
-            store.features(m, z=cols["z"] if m == "physics" else None, out=outs[m])
+            store.features(m, z=cols["z"] if m == "physics" else None, out=outs[m],
+                           status=gp_status if m == "gp2d" else None)
             w = _native.COLS[m]
             table[:, c0:c0 + w].copy_(outs[m])
             c0 += w
@@ -313,6 +315,21 @@ def run_gpu_arm(args):
                     "traffic_source": "ncu --set full capture at 200k objects (profiles/r01_stat_v2_full.txt), scaled per object",
                     "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s",
                     "algorithmic_bytes_per_launch": algorithmic_bytes(n_rows, n_obj), "ms_per_launch": stat_ms}
+        roof_gp = None
+        if gp_status is not None and pass_ms.get("gp2d"):
+            # dominant kernel of the step: FP64 work of the GP = (evaluations + the one at the optimum) x N^3 flop
+            # (N^3/2 FMA per -lnL + gradient evaluation) over its CUDA-event time
+            stt = gp_status.to(torch.float64)
+            fitted = stt[:, 3] >= 10
+            flop = float((((stt[:, 1] + 1.0) * stt[:, 3] ** 3)[fitted]).sum())
+            gp_ms = pass_ms["gp2d"] / args.steps
+            ach_tf = flop / (gp_ms * 1e-3) / 1e12
+            roof_gp = {"kernel": "k_gp2d (2-D GP, 61 % of the step)", "bound": "tensor", "achieved": ach_tf, "peak": 37.1,
+                       "unit": "TFLOP/s", "frac": ach_tf / 37.1, "traffic": None,
+                       "peak_source": "FP64 DMMA/DFMA rate measured on this pool's B200 with tests/micro/fp64_rates.cu "
+                                      "(64 FMA/clk/SM); MEASURED_PEAKS.json has no FP64 figure",
+                       "algorithmic_flop_per_launch": flop, "ms_per_launch": gp_ms,
+                       "mean_evaluations": float(stt[:, 1][fitted].mean()), "mean_points": float(stt[:, 3][fitted].mean())}
         cpu = None
         if not args.no_cpu:
             cores = os.cpu_count() or 1
@@ -331,7 +348,7 @@ def run_gpu_arm(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps},
             "gpu_launches": int(launches),
-            "roofline": roof, "cpu_baseline": cpu,
+            "roofline": roof, "roofline_dominant": roof_gp, "cpu_baseline": cpu,
             "passes": {k: {"ms_per_step": v / args.steps, "share": v / ms} for k, v in pass_ms.items() if v > 0},
             "observations_per_gpu": n_rows,
         }
