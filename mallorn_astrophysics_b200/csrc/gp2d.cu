@@ -28,12 +28,18 @@
 namespace mlrn {
 namespace {
 
-constexpr int GP_THREADS = 512;
+#ifndef GP_THREADS_N
+#define GP_THREADS_N 512
+#endif
+#ifndef GP_T_SMEM_MAX
+#define GP_T_SMEM_MAX 12
+#endif
+constexpr int GP_THREADS = GP_THREADS_N;
 constexpr int GP_WARPS = GP_THREADS / 32;
 constexpr int TB = 16;                 // tile edge
 constexpr int TT = TB * TB;            // doubles per tile
 constexpr int GP_COLS = 27;
-constexpr int T_SMEM_MAX = 12;         // 78 tiles + V buffer + vectors < 227 KB  (N <= 192 in shared memory)
+constexpr int T_SMEM_MAX = GP_T_SMEM_MAX;         // 78 tiles + V buffer + vectors < 227 KB  (N <= 192 in shared memory)
 constexpr int VLD = 20;                // k-row stride of a V tile: 8-word skew per row keeps the DMMA fragment loads conflict-free
 constexpr int VT = TB * VLD;           // doubles per V tile
 constexpr double GP_TINY = 1.25e-12;   // george's frozen white-noise floor
@@ -49,8 +55,8 @@ __host__ __device__ inline size_t gp_fixed_doubles(int np) {
 }
 __host__ __device__ inline size_t gp_tile_doubles(int T) { return (size_t)n_tiles(T) * TT + (size_t)T * VT; }
 __host__ inline size_t gp_smem_bytes(int T, bool tiles_in_smem) {
-  size_t d = gp_fixed_doubles(T * TB);
-  if (tiles_in_smem) d += gp_tile_doubles(T);
+  size_t d = gp_fixed_doubles(T * TB) + (size_t)T * VT;        // the V buffer is always in shared memory
+  if (tiles_in_smem) d += (size_t)n_tiles(T) * TT;
   return d * sizeof(double) + 2 * n_tiles(T) + 64;      // + (I, J) byte table of the tiles
 }
 
@@ -383,7 +389,7 @@ __device__ __forceinline__ void gp_eval(const GpShared& S, double* __restrict__ 
 }
 
 template <bool SMEM_TILES>
-__global__ void __launch_bounds__(GP_THREADS, 1)
+__global__ void __launch_bounds__(GP_THREADS, (GP_THREADS <= 256) ? 2 : 1)
 k_gp2d(const long long* __restrict__ seg_off, const double* __restrict__ gt, const double* __restrict__ gf,
        const double* __restrict__ ge, const unsigned short* __restrict__ grank, int n_obj, int T_cap, int n_lo,
        int n_hi, double* __restrict__ gscratch, double* __restrict__ gcache, unsigned long long* __restrict__ ticket, double* __restrict__ out,
@@ -403,8 +409,9 @@ k_gp2d(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
     S.Lc = d; d += TT;
     S.Li = d; d += 2 * TT; S.LiT = d; d += 2 * VT; S.w = d; d += 2 * TB;      // double-buffered (look-ahead)
     S.red = d; d += GP_WARPS * 4; S.bc = d; d += 16;
-    if (SMEM_TILES) { S.tiles = d; d += (size_t)n_tiles(T_cap) * TT; S.vbuf = d; d += (size_t)T_cap * VT; }
-    else { S.tiles = gscratch + (size_t)blockIdx.x * gp_tile_doubles(T_cap); S.vbuf = S.tiles + (size_t)n_tiles(T_cap) * TT; }
+    S.vbuf = d; d += (size_t)T_cap * VT;
+    if (SMEM_TILES) { S.tiles = d; d += (size_t)n_tiles(T_cap) * TT; }
+    else S.tiles = gscratch + (size_t)blockIdx.x * n_tiles(T_cap) * TT;
     S.tI = (unsigned char*)d; S.tJ = S.tI + n_tiles(T_cap);
     // address-space hints: everything carved from the dynamic shared array is shared memory
     __builtin_assume(__isShared(S.st)); __builtin_assume(__isShared(S.sl)); __builtin_assume(__isShared(S.sy));
@@ -414,7 +421,8 @@ k_gp2d(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
     __builtin_assume(__isShared(S.w));
     __builtin_assume(__isShared(S.red)); __builtin_assume(__isShared(S.bc));
     __builtin_assume(__isShared(S.tI)); __builtin_assume(__isShared(S.tJ));
-    if (SMEM_TILES) { __builtin_assume(__isShared(S.tiles)); __builtin_assume(__isShared(S.vbuf)); }
+    __builtin_assume(__isShared(S.vbuf));
+    if (SMEM_TILES) __builtin_assume(__isShared(S.tiles));
   }
   for (int tl = tid; tl < n_tiles(T_cap); tl += GP_THREADS) {
     int I = (int)((sqrt(8.0 * tl + 1.0) - 1.0) * 0.5);
@@ -551,8 +559,8 @@ k_gp2d(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
     if (s_pk < 0) continue;
     const double pt = gt[base + s_pk] - tmin_all;
     const KernelPars kp = unpack(p);
-    if (warp < 12) {                                   // 12 predictions, one warp each (:236-262)
-      const int ei = warp / 3, j = warp % 3;
+    for (int pw = warp; pw < 12; pw += GP_WARPS) {     // 12 predictions, one warp each (:236-262)
+      const int ei = pw / 3, j = pw % 3;
       const double ep = (ei == 0) ? 0.0 : (ei == 1 ? 20.0 : (ei == 2 ? 50.0 : 100.0));
       const double tq = pt + ep, lq = c_wave[1 + j];
       double acc = 0.0;
@@ -562,7 +570,7 @@ k_gp2d(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
         acc += kp.amp * (1.0 + s) * exp(-s) * S.sb[i];
       }
       for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
-      if (lane == 0) S.bc[warp] = (acc + kp.mean) * scale;
+      if (lane == 0) S.bc[pw] = (acc + kp.mean) * scale;
     }
     __syncthreads();
     if (tid == 0) {
@@ -594,26 +602,28 @@ int run_gp2d(const mlrn_store* s, double* out_dev, int* status_dev, cudaStream_t
   if (s->n_obj == 0) return MLRN_OK;
   const int T_need = (s->max_obs + TB - 1) / TB > 1 ? (s->max_obs + TB - 1) / TB : 1;
   const int T1 = T_need < T_SMEM_MAX ? T_need : T_SMEM_MAX;
-  const int grid = s->n_obj < s->sm_count ? s->n_obj : s->sm_count;
+  const size_t smem1 = gp_smem_bytes(T1, true), smem2 = gp_smem_bytes(T_need, false);
+  MLRN_CUDA(cudaFuncSetAttribute(k_gp2d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+  MLRN_CUDA(cudaFuncSetAttribute(k_gp2d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+  int occ1 = 1, occ2 = 1;
+  MLRN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_gp2d<true>, GP_THREADS, smem1));
+  MLRN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_gp2d<false>, GP_THREADS, smem2));
+  if (occ1 < 1) occ1 = 1;
+  if (occ2 < 1) occ2 = 1;
+  auto grid_for = [&](int occ) { long long g = (long long)s->sm_count * occ; return (int)(s->n_obj < g ? s->n_obj : g); };
+  const int grid1 = grid_for(occ1), grid2 = grid_for(occ2), gmax = grid1 > grid2 ? grid1 : grid2;
   double* cache = nullptr;                              // s / exp(-s) of the current evaluation, per CTA (L2-resident)
-  MLRN_CUDA(cudaMallocAsync(&cache, sizeof(double) * 2 * (size_t)n_tiles(T_need) * TT * grid, st));
-  {
-    const size_t smem = gp_smem_bytes(T1, true);
-    MLRN_CUDA(cudaFuncSetAttribute(k_gp2d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MLRN_CUDA(cudaMemsetAsync(s->ticket + 2, 0, 2 * sizeof(unsigned long long), st));
-    k_gp2d<true><<<grid, GP_THREADS, smem, st>>>(s->seg_off, s->t, s->flux, s->err, s->rank, s->n_obj, T1, 0, T1 * TB,
+  MLRN_CUDA(cudaMallocAsync(&cache, sizeof(double) * 2 * (size_t)n_tiles(T_need) * TT * gmax, st));
+  MLRN_CUDA(cudaMemsetAsync(s->ticket + 2, 0, 2 * sizeof(unsigned long long), st));
+  k_gp2d<true><<<grid1, GP_THREADS, smem1, st>>>(s->seg_off, s->t, s->flux, s->err, s->rank, s->n_obj, T1, 0, T1 * TB,
                                                  nullptr, cache, s->ticket + 2, out_dev, status_dev);
-    MLRN_CUDA(cudaGetLastError());
-    count_launch();
-  }
-  if (T_need > T_SMEM_MAX) {                            // long objects: tiles in global scratch
-    const size_t smem = gp_smem_bytes(T_need, false);
-    MLRN_CUDA(cudaFuncSetAttribute(k_gp2d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MLRN_CUDA(cudaGetLastError());
+  count_launch();
+  if (T_need > T_SMEM_MAX) {                            // objects beyond the shared-memory capacity: tiles in an L2-resident scratch
     double* scratch = nullptr;
-    const size_t per_cta = gp_tile_doubles(T_need) * sizeof(double);
-    MLRN_CUDA(cudaMallocAsync(&scratch, per_cta * grid, st));
-    k_gp2d<false><<<grid, GP_THREADS, smem, st>>>(s->seg_off, s->t, s->flux, s->err, s->rank, s->n_obj, T_need,
-                                                  T1 * TB + 1, T_need * TB, scratch, cache, s->ticket + 3, out_dev, status_dev);
+    MLRN_CUDA(cudaMallocAsync(&scratch, sizeof(double) * (size_t)n_tiles(T_need) * TT * grid2, st));
+    k_gp2d<false><<<grid2, GP_THREADS, smem2, st>>>(s->seg_off, s->t, s->flux, s->err, s->rank, s->n_obj, T_need,
+                                                   T1 * TB + 1, T_need * TB, scratch, cache, s->ticket + 3, out_dev, status_dev);
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(scratch, st);
     if (e != cudaSuccess) { cudaFreeAsync(cache, st); return cuda_fail(e, "k_gp2d<global> launch"); }
