@@ -47,7 +47,8 @@ k_pass(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
   double* scr = se + np;
   unsigned short* srank = (unsigned short*)(scr + (size_t)NS * np);
 
-  for (long long o = (long long)blockIdx.x * PASS_WARPS + warp; o < n_obj; o += (long long)gridDim.x * PASS_WARPS) {
+  const int nwarps = blockDim.x >> 5;     // 4, or fewer when long objects need more scratch per warp
+  for (long long o = (long long)blockIdx.x * nwarps + warp; o < n_obj; o += (long long)gridDim.x * nwarps) {
     ObjView v;
     stage_object(tm, seg_off, gt, gf, ge, grank, o, st, sf, se, srank, v);
     if (PASS == PASS_COLOR) color_row(tm, v, scr, scr + np, row);
@@ -65,15 +66,17 @@ template <int PASS>
 int launch_pass(const mlrn_store* s, const double* z, double* out, cudaStream_t st) {
   if (s->n_obj == 0) return MLRN_OK;
   const int np = next_pow2(s->max_obs > 64 ? s->max_obs : 64);   // scratch also holds small fixed tables
-  const size_t smem = pass_bytes_per_warp(np, PassTraits<PASS>::scratch) * PASS_WARPS;
+  int warps = PASS_WARPS;
+  while (warps > 1 && pass_bytes_per_warp(np, PassTraits<PASS>::scratch) * warps > 200 * 1024) warps >>= 1;
+  const size_t smem = pass_bytes_per_warp(np, PassTraits<PASS>::scratch) * warps;
   MLRN_CUDA(cudaFuncSetAttribute(k_pass<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  MLRN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pass<PASS>, PASS_WARPS * 32, smem));
+  MLRN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pass<PASS>, warps * 32, smem));
   if (per_sm < 1) per_sm = 1;
-  long long want = ((long long)s->n_obj + PASS_WARPS - 1) / PASS_WARPS;
+  long long want = ((long long)s->n_obj + warps - 1) / warps;
   long long cap = (long long)s->sm_count * per_sm;
   int grid = (int)(want < cap ? want : cap);
-  k_pass<PASS><<<grid, PASS_WARPS * 32, smem, st>>>(s->seg_off, s->t, s->flux, s->err, s->rank, z, s->n_obj, np, out);
+  k_pass<PASS><<<grid, warps * 32, smem, st>>>(s->seg_off, s->t, s->flux, s->err, s->rank, z, s->n_obj, np, out);
   MLRN_CUDA(cudaGetLastError());
   count_launch();
   return MLRN_OK;

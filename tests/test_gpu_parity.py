@@ -135,3 +135,26 @@ def test_object_above_cap_is_rejected():
     with pytest.raises(_native.MallornNativeError):
         LightCurveStore(np.zeros(n, np.int32), np.zeros(n, np.uint8), np.arange(n, dtype=float),
                         np.ones(n), np.ones(n), 1)
+
+
+def test_long_objects_up_to_the_cap():
+    """A few objects near the 1024-observation cap (far beyond survey cadence): every pass must still run, and
+    the scalar passes must still match the oracle."""
+    from mallorn_astrophysics_b200.store import LightCurveStore
+    from mallorn_astrophysics_b200.synth import make_table
+    from oracle.extract import run_table
+    from mallorn_astrophysics_b200.synth import LightCurveTable
+    base = make_table(12, seed=321, count_scale=2.5)           # ~375 observations each (the generator clips at 400) ...
+    table = LightCurveTable((base.obj // 2).astype(np.int32), base.band, base.t, base.flux, base.err, 6,   # ... merged in pairs
+                            base.z[::2].copy(), base.ebv[::2].copy(), base.label[::2].copy(), "long")
+    assert 512 < np.bincount(table.obj).max() <= 1024
+    with LightCurveStore.from_table(table) as s:
+        assert s.max_obs > 512
+        got = {m: s.features(m, z=table.z if m == "physics" else None)
+               for m in ("statistical", "colors", "shape", "tde", "physics", "bazin", "powerlaw", "gp2d")}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for m in ("statistical", "colors", "shape", "tde", "physics"):
+            present, want = run_table(m, table)
+            _compare(got[m][present], want, rtol=1e-5, atol=1e-9, what=f"{m}/long")
+    assert np.isfinite(got["gp2d"][:, 0]).all() and np.isfinite(got["bazin"][:, 8 * 2]).any()
