@@ -27,23 +27,23 @@ k_bazin_thread(const long long* __restrict__ seg_off, const double* __restrict__
     for (int tries = 0; tries < 4 && !active && !exhausted; ++tries) {
       fit = (long long)atomicAdd(ticket, 1ULL);
       if (fit >= total) { exhausted = true; break; }
-      const long long o = fit / N_BAND; const int b = (int)(fit % N_BAND);
+      const int b = (int)(fit / n_obj); const long long o = fit % n_obj;    // band-major: lanes of a warp get bands of similar length
       const long long lo = seg_off[o * N_SEG + b];
       const int n = (int)(seg_off[o * N_SEG + b + 1] - lo);
       int code;
       active = job.init(gt + lo, gf + lo, ge + lo, n, code);
       if (!active) {
         job.finish(code, out + o * BAZIN_COLS + 8 * b);
-        if (status) { status[fit * 2] = code; status[fit * 2 + 1] = 0; }
+        if (status) { status[(o * N_BAND + b) * 2] = code; status[(o * N_BAND + b) * 2 + 1] = 0; }
       }
     }
     if (!__syncthreads_or(active || !exhausted)) break;      // also lines the warps up: they fetch the same code
     if (active) {
       const int rc = job.step();
       if (rc != TRF_RUNNING) {
-        const long long o = fit / N_BAND; const int b = (int)(fit % N_BAND);
+        const int b = (int)(fit / n_obj); const long long o = fit % n_obj;
         job.finish(rc, out + o * BAZIN_COLS + 8 * b);
-        if (status) { status[fit * 2] = rc; status[fit * 2 + 1] = job.trf.nfev; }
+        if (status) { status[(o * N_BAND + b) * 2] = rc; status[(o * N_BAND + b) * 2 + 1] = job.trf.nfev; }
         active = false;
       }
     }
@@ -75,8 +75,9 @@ k_decline_thread(const long long* __restrict__ seg_off, const double* __restrict
   DeclineJob<KIND> job;
   bool active = false, exhausted = false;
   long long fit = 0;
+  // (band, model)-major ticket order: the lanes of a warp fit the same model to the same band of different objects
   auto slot = [&](long long ft) {                     // column of this fit inside the 27-wide row
-    const long long o = ft / (3 * PER_BAND); const int rem = (int)(ft % (3 * PER_BAND));
+    const int rem = (int)(ft / n_obj); const long long o = ft % n_obj;
     const int j = rem / PER_BAND, q = (KIND == 0) ? rem % PER_BAND : (KIND == 1 ? 7 : 8);
     return o * POWERLAW_COLS + 9 * j + q;
   };
@@ -84,7 +85,7 @@ k_decline_thread(const long long* __restrict__ seg_off, const double* __restrict
     for (int tries = 0; tries < 4 && !active && !exhausted; ++tries) {
       fit = (long long)atomicAdd(ticket, 1ULL);
       if (fit >= total) { exhausted = true; break; }
-      const long long o = fit / (3 * PER_BAND); const int rem = (int)(fit % (3 * PER_BAND));
+      const int rem = (int)(fit / n_obj); const long long o = fit % n_obj;
       const int j = rem / PER_BAND, q = rem % PER_BAND;
       const int band = (j == 0) ? BG : (j == 1 ? BR : BI);
       const long long lo = seg_off[o * N_SEG + band];
