@@ -1,6 +1,9 @@
-// stat.cuh -- the moment pass: 17 statistics x (6 bands + all) + 3 flux ratios + peak_band.
+// stat.cuh -- the moment pass, team-generic statement: 17 statistics x (6 bands + all) + 3 flux ratios + peak_band.
 // Mirrors the behaviour of reference src/features/statistical.py:41-132 (compute_band_statistics)
 // and :185-222 (cross-band tail); output order = schema.STAT_COLUMNS.
+// The GPU kernel that ships is stat_fast.cu (register sorts, window-search MAD, merge of the band runs); this
+// straightforward version defines the column layout constants both share and is what tests/hostsim instantiates
+// on the CPU to check the semantics line by line against the reference goldens.
 #pragma once
 #include "objview.cuh"
 

@@ -44,13 +44,13 @@ def _pack(g):
     return pack_reference(g["obj"], g["band"], g["t"], g["flux"], g["err"], n_obj), n_obj
 
 
-@pytest.mark.parametrize("module,fn,ncol", [("colors", "hs_color", 83), ("shape", "hs_shape", 65),
+@pytest.mark.parametrize("module,fn,ncol", [("statistical", "hs_stat", 123), ("colors", "hs_color", 83), ("shape", "hs_shape", 65),
                                             ("tde", "hs_tde", 25), ("physics", "hs_physics", 32)])
 @pytest.mark.parametrize("fixture", ["ref_sparse", "ref_edge"])
 def test_scalar_templates_match_reference(golden, hs, fixture, module, fn, ncol):
     g = golden[fixture]
     pk, n_obj = _pack(g)
-    out, _ = _run(hs, fn, ncol, pk, n_obj, z=g["z"])
+    out, _ = _run(hs, fn, ncol, pk, n_obj, z=None if module == "statistical" else g["z"])
     pres, ref = g[f"{module}_present"], g[f"{module}_rows"]
     keep = pres != (TIE_OBJECT if fixture == "ref_edge" else -1)
     got, ref = out[pres][keep], ref[keep]
