@@ -8,18 +8,20 @@
 
 namespace mlrn {
 
-// k-th smallest (0-based) of a[0..n) by rank counting (ties broken by index); O(n^2) compares, no scratch
-MLRN_FN double kth_smallest(const double* a, int n, int k) {
-  for (int i = 0; i < n; ++i) {
+// numpy.median of a[0..n) without scratch: one rank-counting sweep (ties broken by index) that picks up both middle
+// order statistics at once; O(n^2) compares, n is a band length
+MLRN_FN double median_unsorted(const double* a, int n) {
+  const int k_hi = n >> 1, k_lo = (n & 1) ? k_hi : k_hi - 1;
+  double lo = qnan(), hi = qnan();
+  int found = 0;
+  for (int i = 0; i < n && found < 2; ++i) {
     const double v = a[i];
     int rk = 0;
     for (int j = 0; j < n; ++j) { const double u = a[j]; rk += (u < v) || (u == v && j < i); }
-    if (rk == k) return v;
+    if (rk == k_lo) { lo = v; ++found; if (k_hi == k_lo) { hi = v; ++found; } }
+    else if (rk == k_hi) { hi = v; ++found; }
   }
-  return qnan();
-}
-MLRN_FN double median_unsorted(const double* a, int n) {
-  return (n & 1) ? kth_smallest(a, n, n >> 1) : 0.5 * (kth_smallest(a, n, (n >> 1) - 1) + kth_smallest(a, n, n >> 1));
+  return (n & 1) ? hi : 0.5 * (lo + hi);
 }
 
 struct BazinJob {
