@@ -15,6 +15,8 @@ library exports (statistical, colors, shape, tde_physics, physics_based, bazin, 
              the step; ``passes`` lists every pass's share of the step.
 * ``cpu_baseline`` the CPU oracle (``oracle/``: the reference's numpy/scipy arithmetic) on a bounded
              sample of the same workload, all host cores.
+* ``widened``  SURVEY 8(f) rows built so far, timed beside the step on a slice of the same batch: the per-band
+             1-D GP pass (``extract_gp_features``, 21 columns); not part of ``value`` (the 434-column table).
 * ``--impl reference`` times only that CPU path (the reference has no GPU path and, being a Python
              package with no native code, "the reference's own CPU implementation" is the oracle
              restatement: ``/root/reference`` does not exist on the GPU box).
@@ -37,6 +39,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+MODULE_WIDTH = {"statistical": 123, "colors": 83, "shape": 65, "tde": 25, "physics": 32, "bazin": 52, "powerlaw": 27,
+                "gp2d": 27, "gp1d": 21}
 MODULES = ("statistical", "colors", "shape", "tde", "physics", "bazin", "powerlaw", "gp2d")
 METRIC = "light curves/sec for the 222-feature set (full 434-column module table)"
 UNIT = "objects/s"
@@ -165,7 +169,7 @@ def workload_config(args, objects_per_gpu, modules):
             if objects_per_gpu == 1_000_000 else
             f"C4 generator at {objects_per_gpu} objects per GPU (BASELINE.json configs[3] shape)",
             "objects_per_gpu": objects_per_gpu, "bands": 6, "mean_obs_per_object": 150,
-            "modules": list(modules), "columns": 434,
+            "modules": list(modules), "columns": sum(MODULE_WIDTH[m] for m in modules),
             "l2": "inputs larger than L2 (no flush needed)" if objects_per_gpu * 150 * 25 > 2 * 126e6 else
                   "L2 flushed between steps",
             "parallelism": f"objects sharded over {args.gpus} GPU(s), all-gather of the feature table"}
@@ -196,11 +200,10 @@ def run_gpu_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L = _native.lib()
-    modules = [m for m in MODULES if hasattr(L, {"statistical": "mlrn_stat", "colors": "mlrn_color",
-               "shape": "mlrn_shape", "tde": "mlrn_tde", "physics": "mlrn_physics", "bazin": "mlrn_bazin",
-               "powerlaw": "mlrn_powerlaw", "gp2d": "mlrn_gp2d"}[m])]
-    if args.modules:
-        modules = [m for m in modules if m in args.modules.split(",")]
+    symbol = {"statistical": "mlrn_stat", "colors": "mlrn_color", "shape": "mlrn_shape", "tde": "mlrn_tde",
+              "physics": "mlrn_physics", "bazin": "mlrn_bazin", "powerlaw": "mlrn_powerlaw", "gp2d": "mlrn_gp2d",
+              "gp1d": "mlrn_gp1d"}
+    modules = [m for m in (args.modules.split(",") if args.modules else MODULES) if hasattr(L, symbol[m])]
     n_obj = args.objects
     cols = make_columns_device(n_obj, SEED * 131 + rank, dev)
     n_rows = int(cols["obj"].shape[0])
@@ -211,6 +214,7 @@ def run_gpu_arm(args):
     table = torch.empty((n_obj, width), dtype=torch.float64, device=dev)
     gathered = torch.empty((world * n_obj, width), dtype=torch.float64, device=dev) if world > 1 else None
     gp_status = torch.zeros((n_obj, 4), dtype=torch.int32, device=dev) if "gp2d" in modules else None
+    gp1_status = torch.zeros((n_obj, 12), dtype=torch.int32, device=dev) if "gp1d" in modules else None
     flush = None
     if n_rows * 25 < 2 * 126e6:
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -229,7 +233,7 @@ def run_gpu_arm(args):
         c0 = 0
         for m in modules:
             store.features(m, z=cols["z"] if m == "physics" else None, out=outs[m],
-                           status=gp_status if m == "gp2d" else None)
+                           status=gp_status if m == "gp2d" else (gp1_status if m == "gp1d" else None))
             w = _native.COLS[m]
             table[:, c0:c0 + w].copy_(outs[m])
             c0 += w
@@ -298,6 +302,31 @@ def run_gpu_arm(args):
         e2e_s = float(tms.item())
     e2e_value = world * n_obj * e2e_steps / e2e_s
 
+    # ---- section 8(f) row measured beside the step: the per-band 1-D GP pass (extract_gp_features), on a bounded slice
+    widened = None
+    if hasattr(L, "mlrn_gp1d") and "gp1d" not in modules and not args.modules and args.gp1d_objects > 0:
+        k = min(n_obj, args.gp1d_objects)
+        keep = cols["obj"] < k
+        sub = {c: cols[c][keep].contiguous() for c in ("obj", "band", "t", "flux", "err")}
+        o1 = torch.empty((k, _native.COLS["gp1d"]), dtype=torch.float64, device=dev)
+        s1 = torch.zeros((k, 12), dtype=torch.int32, device=dev)
+        st1 = LightCurveStore(sub["obj"], sub["band"], sub["t"], sub["flux"], sub["err"], k, device=local, stream=sptr)
+        st1.features("gp1d", out=o1, status=s1)                       # warm-up
+        a, b = ev(), ev()
+        a.record(stream)
+        st1.features("gp1d", out=o1, status=s1)
+        b.record(stream)
+        stream.synchronize()
+        st1.close()
+        gms = a.elapsed_time(b)
+        fitted = int((s1[:, 2::3] >= 0).sum())
+        evals = int(s1[:, 0::3].sum())
+        widened = {"gp1d": {"reference": "extract_gp_features (gaussian_process.py:251), 21 columns", "objects": k,
+                            "ms": gms, "objects_per_s": k / (gms * 1e-3), "bands_fitted": fitted,
+                            "objective_evaluations": evals, "evaluations_per_s": evals / (gms * 1e-3),
+                            "observations": int(sub["obj"].shape[0]), "launches": 1}}
+        del sub, o1, s1
+
     if rank == 0:
         peaks = {}
         try:
@@ -351,6 +380,7 @@ def run_gpu_arm(args):
             "roofline": roof, "roofline_dominant": roof_gp, "cpu_baseline": cpu,
             "passes": {k: {"ms_per_step": v / args.steps, "share": v / ms} for k, v in pass_ms.items() if v > 0},
             "observations_per_gpu": n_rows,
+            "widened": widened,
         }
         print(json.dumps(out))
     if world > 1:
@@ -367,6 +397,8 @@ def main():
     ap.add_argument("--modules", default="", help="comma list; default = every pass the library exports")
     ap.add_argument("--cpu-objects", type=int, default=0, help="CPU sample size (default scales with host cores)")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--gp1d-objects", type=int, default=200_000,
+                    help="objects of the batch the per-band GP pass (SURVEY 8f row 2) is timed on beside the step; 0 = skip")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":

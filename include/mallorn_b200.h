@@ -41,6 +41,7 @@ extern "C" {
 #define MLRN_BAZIN_COLS 52      /* extract_bazin_features         bazin_fitting.py:254    */
 #define MLRN_POWERLAW_COLS 27   /* extract_powerlaw_features      scripts/train_v55_powerlaw.py:196 */
 #define MLRN_GP2D_COLS 27       /* extract_multiband_gp_features  multiband_gp.py:347     */
+#define MLRN_GP1D_COLS 21       /* extract_gp_features            gaussian_process.py:251 */
 #define MLRN_SEGMETA_COLS 22    /* K1 integer outputs per object, see mlrn_store_segments */
 
 typedef struct mlrn_store mlrn_store;   /* packed, device-resident light curves of one batch */
@@ -87,6 +88,11 @@ int mlrn_bazin(const mlrn_store* s, double* out, int32_t* status, int out_on_dev
 int mlrn_powerlaw(const mlrn_store* s, double* out, int32_t* status, int out_on_device, void* stream);
 /* status (optional): int32 [n_obj, 4] = {L-BFGS-B iterations, function evaluations, termination code, N used} */
 int mlrn_gp2d(const mlrn_store* s, double* out, int32_t* status, int out_on_device, void* stream);
+/* per-band 1-D GP (sklearn GaussianProcessRegressor in the reference: ConstantKernel * RBF + WhiteKernel, four
+ * bounded L-BFGS-B starts per band, gaussian_process.py:29-146) for g, r, i, z plus the cross-band columns.
+ * status (optional): int32 [n_obj, 4, 3] = per band {objective evaluations over the four starts, L-BFGS-B
+ * iterations over the four starts, index of the winning start (-1: band not fitted)} */
+int mlrn_gp1d(const mlrn_store* s, double* out, int32_t* status, int out_on_device, void* stream);
 
 #ifdef __cplusplus
 }

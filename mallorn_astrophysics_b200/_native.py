@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MLRN_LIB") or os.path.join(HERE, "libmallorn_b200.so")   # MLRN_LIB: developer builds (profiling flags)
 
 COLS = {"statistical": 123, "colors": 83, "shape": 65, "tde": 25, "physics": 32,
-        "bazin": 52, "powerlaw": 27, "gp2d": 27}
+        "bazin": 52, "powerlaw": 27, "gp2d": 27, "gp1d": 21}
 SEGMETA_COLS = 22
 N_SEG = 7
 MAX_OBS = 1024
@@ -52,7 +52,7 @@ def lib() -> C.CDLL:
             getattr(L, name).argtypes = [vp, vp, C.c_int, vp]
     if hasattr(L, "mlrn_physics"):
         L.mlrn_physics.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp]
-    for name in ("mlrn_bazin", "mlrn_powerlaw", "mlrn_gp2d"):
+    for name in ("mlrn_bazin", "mlrn_powerlaw", "mlrn_gp2d", "mlrn_gp1d"):
         if hasattr(L, name):
             getattr(L, name).argtypes = [vp, vp, vp, C.c_int, vp]
     _lib = L

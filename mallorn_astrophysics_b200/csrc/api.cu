@@ -27,6 +27,7 @@ int run_physics(const mlrn_store* s, const double* z_dev, double* out_dev, cudaS
 int run_bazin(const mlrn_store* s, double* out_dev, int* status_dev, cudaStream_t st);
 int run_powerlaw(const mlrn_store* s, double* out_dev, int* status_dev, cudaStream_t st);
 int run_gp2d(const mlrn_store* s, double* out_dev, int* status_dev, cudaStream_t st);
+int run_gp1d(const mlrn_store* s, double* out_dev, int* status_dev, cudaStream_t st);
 }  // namespace mlrn
 
 using mlrn::set_error;
@@ -234,6 +235,11 @@ int mlrn_gp2d(const mlrn_store* s, double* out, int32_t* status, int out_on_devi
   cudaStream_t st = (cudaStream_t)stream;
   return with_status(s, out, status, out_on_device, MLRN_GP2D_COLS, 4, st,
                      [&](double* d, int32_t* ds) { return mlrn::run_gp2d(s, d, ds, st); });
+}
+int mlrn_gp1d(const mlrn_store* s, double* out, int32_t* status, int out_on_device, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  return with_status(s, out, status, out_on_device, MLRN_GP1D_COLS, 12, st,
+                     [&](double* d, int32_t* ds) { return mlrn::run_gp1d(s, d, ds, st); });
 }
 
 }  // extern "C"

@@ -21,8 +21,10 @@ def _request_index(ids, object_ids):
     return ids.get_indexer(pd.Series(list(object_ids), dtype=object))
 
 
-def run_frame_module(module: str, lightcurves, object_ids: Optional[Sequence] = None, metadata=None,
-                     device: int = 0):
+def run_frame_modules(modules: Sequence[str], lightcurves, object_ids: Optional[Sequence] = None, metadata=None,
+                      device: int = 0) -> dict:
+    """Pack once (K1), run every pass of ``modules`` on the same device-resident store, return ``{module: DataFrame}``
+    with the reference's per-module schema."""
     import pandas as pd
     if object_ids is None:
         object_ids = lightcurves["object_id"].unique()
@@ -30,27 +32,34 @@ def run_frame_module(module: str, lightcurves, object_ids: Optional[Sequence] = 
     store, ids = LightCurveStore.from_frame(lightcurves, object_ids, device=device)
     try:
         z = None
-        if module == "physics":
+        if "physics" in modules:
             # z_lookup = dict(zip(metadata['object_id'], metadata['Z'])): the LAST duplicate wins
             # (physics_based.py:481); ids missing from the metadata get NaN (:496)
             zmap = pd.Series(metadata["Z"].to_numpy(dtype=np.float64), index=metadata["object_id"].to_numpy())
             zmap = zmap[~zmap.index.duplicated(keep="last")]
             z = zmap.reindex(ids).to_numpy(dtype=np.float64)
-        rows = store.features(module, z=z)
+        rows = {m: store.features(m, z=z if m == "physics" else None) for m in modules}
         counts = store.segments()[:, 0:21:3].sum(axis=1)
     finally:
         store.close()
     req = _request_index(ids, object_ids)
     req = req[counts[req] > 0]                       # drop ids with no observations
-    cols = schema.MODULE_COLUMNS[module]
-    df = pd.DataFrame(rows[req], columns=cols)
     id_col = np.asarray(ids, dtype=object)[req]
-    if module == "statistical":
-        for c in schema.STAT_INT_COLUMNS:
-            df[c] = df[c].astype(np.int64)
-        df.insert(0, "object_id", id_col)
-    elif module == "powerlaw":
-        df.insert(0, "object_id", id_col)            # train_v55_powerlaw.py:197
-    else:
-        df["object_id"] = id_col
-    return df
+    frames = {}
+    for module in modules:
+        df = pd.DataFrame(rows[module][req], columns=schema.MODULE_COLUMNS[module])
+        if module == "statistical":
+            for c in schema.STAT_INT_COLUMNS:
+                df[c] = df[c].astype(np.int64)
+            df.insert(0, "object_id", id_col)
+        elif module == "powerlaw":
+            df.insert(0, "object_id", id_col)        # train_v55_powerlaw.py:197
+        else:
+            df["object_id"] = id_col
+        frames[module] = df
+    return frames
+
+
+def run_frame_module(module: str, lightcurves, object_ids: Optional[Sequence] = None, metadata=None,
+                     device: int = 0):
+    return run_frame_modules([module], lightcurves, object_ids, metadata, device)[module]

@@ -100,12 +100,18 @@ GP2D_COLUMNS = (
     + ["gp_gr_slope_50d", "gp_gr_slope_100d"]
 )
 
+GP1D_BANDS = ["g", "r", "i", "z"]                  # gaussian_process.py:187
+GP1D_COLUMNS = (
+    [f"{b}_{s}" for b in GP1D_BANDS for s in ("gp_length_scale", "gp_amplitude", "gp_noise", "gp_log_likelihood")]
+    + ["gp_ls_ratio_gr", "gp_ls_ratio_ri", "gp_mean_length_scale", "gp_std_length_scale", "gp_mean_amplitude"]
+)
+
 MODULE_COLUMNS = {
     "statistical": STAT_COLUMNS, "colors": COLOR_COLUMNS, "shape": SHAPE_COLUMNS,
     "tde": TDE_COLUMNS, "physics": PHYSICS_COLUMNS, "bazin": BAZIN_COLUMNS,
-    "powerlaw": POWERLAW_COLUMNS, "gp2d": GP2D_COLUMNS,
+    "powerlaw": POWERLAW_COLUMNS, "gp2d": GP2D_COLUMNS, "gp1d": GP1D_COLUMNS,
 }
 
 assert len(STAT_COLUMNS) == 123 and len(COLOR_COLUMNS) == 83 and len(SHAPE_COLUMNS) == 65
 assert len(TDE_COLUMNS) == 25 and len(PHYSICS_COLUMNS) == 32 and len(BAZIN_COLUMNS) == 52
-assert len(POWERLAW_COLUMNS) == 27 and len(GP2D_COLUMNS) == 27
+assert len(POWERLAW_COLUMNS) == 27 and len(GP2D_COLUMNS) == 27 and len(GP1D_COLUMNS) == 21

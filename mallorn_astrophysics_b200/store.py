@@ -32,6 +32,38 @@ def _ptr(x, dtype):
     return a.ctypes.data, a, False
 
 
+def frame_columns(lightcurves, object_ids: Optional[Sequence] = None):
+    """Host ingest: reference-format long DataFrame -> the flat columns K1 takes.
+
+    ``(obj int32, band uint8, t, flux, err float64, ids)``: ``obj[i]`` is the position of row i's ``object_id`` in
+    ``ids`` (the unique requested ids in request order; default: order of first appearance, as
+    ``lightcurves['object_id'].unique()``), -1 for rows of objects that were not requested or have no id;
+    ``band[i]`` is 0..5 for u g r i z y and ``UNKNOWN_BAND`` for any other ``Filter`` value (NaN included).
+    The strings are hashed once (``pandas.factorize``) and the per-row work is integer gathers; row order is the
+    file order, which K1 preserves inside each object.  Replaces the ``groupby('object_id')`` dict every
+    reference extractor builds (``statistical.py:155`` ...) and the ``Filter == band`` masks.
+    """
+    import pandas as pd
+    row_code, uniq = pd.factorize(lightcurves["object_id"], sort=False)          # -1 for a missing id
+    if object_ids is None:
+        ids = pd.Index(uniq)
+        remap = np.arange(len(uniq), dtype=np.int32)
+    else:
+        ids = pd.Index(pd.unique(pd.Series(list(object_ids), dtype=object)))
+        remap = ids.get_indexer(pd.Index(uniq)).astype(np.int32)                 # -1: present in the frame, not requested
+    obj = np.full(len(row_code), -1, dtype=np.int32)
+    ok = row_code >= 0
+    if len(remap):
+        obj[ok] = remap[row_code[ok]]
+    band_code, band_uniq = pd.factorize(lightcurves["Filter"], sort=False)
+    lut = np.array([BAND_CODE.get(x, UNKNOWN_BAND) for x in band_uniq] + [UNKNOWN_BAND], dtype=np.uint8)
+    band = lut[band_code]                                                         # code -1 (NaN) -> the appended UNKNOWN entry
+    return (obj, band,
+            lightcurves["Time (MJD)"].to_numpy(dtype=np.float64),
+            lightcurves["Flux"].to_numpy(dtype=np.float64),
+            lightcurves["Flux_err"].to_numpy(dtype=np.float64), ids)
+
+
 class LightCurveStore:
     """Packed light curves of ``n_obj`` objects on one GPU."""
 
@@ -65,17 +97,8 @@ class LightCurveStore:
         Returns ``(store, ids)`` where ``ids`` are the unique requested ids in request order; rows
         of other objects are skipped, as the reference's ``grouped.get(obj_id)`` never sees them.
         """
-        import pandas as pd
-        if object_ids is None:
-            object_ids = lightcurves["object_id"].unique()
-        ids = pd.Index(pd.unique(pd.Series(list(object_ids), dtype=object)))
-        codes = ids.get_indexer(lightcurves["object_id"]).astype(np.int32)
-        band = lightcurves["Filter"].map(BAND_CODE).fillna(UNKNOWN_BAND).to_numpy(dtype=np.uint8)
-        store = cls(codes, band,
-                    lightcurves["Time (MJD)"].to_numpy(dtype=np.float64),
-                    lightcurves["Flux"].to_numpy(dtype=np.float64),
-                    lightcurves["Flux_err"].to_numpy(dtype=np.float64), len(ids), device, stream)
-        return store, ids
+        codes, band, t, flux, err, ids = frame_columns(lightcurves, object_ids)
+        return cls(codes, band, t, flux, err, len(ids), device, stream), ids
 
     # ------------------------------------------------------------------ K1 outputs
     def segments(self) -> np.ndarray:
@@ -116,7 +139,7 @@ class LightCurveStore:
                 z = np.full(self.n_obj, np.nan)
             zptr, zkeep, zdev = _ptr(z, np.float64)
             rc = L.mlrn_physics(self._h, zptr, 1 if zdev else 0, optr, 1 if odev else 0, st)
-        elif module in ("bazin", "powerlaw", "gp2d"):
+        elif module in ("bazin", "powerlaw", "gp2d", "gp1d"):
             sptr = 0
             if status is not None:
                 if _is_torch(status):
@@ -127,7 +150,8 @@ class LightCurveStore:
                     if odev or status.dtype != np.int32 or not status.flags.c_contiguous:
                         raise ValueError("status must be a C-contiguous int32 array on the same side as out")
                     sptr = status.ctypes.data
-            fn = getattr(L, {"bazin": "mlrn_bazin", "powerlaw": "mlrn_powerlaw", "gp2d": "mlrn_gp2d"}[module])
+            fn = getattr(L, {"bazin": "mlrn_bazin", "powerlaw": "mlrn_powerlaw", "gp2d": "mlrn_gp2d",
+                              "gp1d": "mlrn_gp1d"}[module])
             rc = fn(self._h, optr, sptr, 1 if odev else 0, st)
         else:
             fn = getattr(L, {"statistical": "mlrn_stat", "colors": "mlrn_color", "shape": "mlrn_shape",

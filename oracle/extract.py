@@ -11,12 +11,12 @@ from typing import Optional, Tuple
 
 import numpy as np
 
-from . import bazin, colors, gp2d, physics, powerlaw, shape, statistical, tde
+from . import bazin, colors, gp1d, gp2d, physics, powerlaw, shape, statistical, tde
 from .common import group_objects
 
-MODULES = ("statistical", "colors", "shape", "tde", "physics", "bazin", "powerlaw", "gp2d")
+MODULES = ("statistical", "colors", "shape", "tde", "physics", "bazin", "powerlaw", "gp2d", "gp1d")
 _WIDTH = {"statistical": 123, "colors": 83, "shape": 65, "tde": 25, "physics": 32,
-          "bazin": 52, "powerlaw": 27, "gp2d": 27, "segments": 22}
+          "bazin": 52, "powerlaw": 27, "gp2d": 27, "gp1d": 21, "segments": 22}
 
 
 def run_module(name: str, obj, band, t, f, e, n_obj: int,
@@ -42,6 +42,8 @@ def run_module(name: str, obj, band, t, f, e, n_obj: int,
             r = powerlaw.object_row(v)
         elif name == "gp2d":
             r = gp2d.object_row(v)
+        elif name == "gp1d":
+            r = gp1d.object_row(v)
         else:
             raise KeyError(name)
         present.append(k)

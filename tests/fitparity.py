@@ -51,3 +51,33 @@ def classify_r2(got, ref):
     c["match"], c["no_worse"], c["worse"] = int(match.sum()), int(no_worse.sum()), int(worse.sum())
     c["worst"] = float(-d[worse].min()) if worse.any() else 0.0
     return c
+
+
+def classify_gp1d(got, ref):
+    """got, ref: [n, 21] per-band GP tables.  One fit per (object, band in g r i z): {length scale, amplitude, noise,
+    log-likelihood}.  ``match``: all four within rtol 1e-3 (atol 1e-6); ``no_worse``: hyper-parameters differ (a flat
+    direction -- typically the white-noise level when the measurement variances dominate) but our log-likelihood
+    is at least the reference's minus 1e-6 relative; ``worse`` otherwise.  ``cross_bad`` counts cross-band
+    columns (ratios / means, 16..20) that disagree although every band they are built from matched."""
+    c = {"fits": 0, "match": 0, "no_worse": 0, "worse": 0, "nan_diff": 0, "worst": 0.0, "cross_bad": 0}
+    for i in range(ref.shape[0]):
+        all_match = True
+        for b in range(4):
+            r, m = ref[i, 4 * b:4 * b + 4], got[i, 4 * b:4 * b + 4]
+            if np.isnan(r).all() and np.isnan(m).all():
+                continue
+            c["fits"] += 1
+            if not np.array_equal(np.isnan(r), np.isnan(m)):
+                c["nan_diff"] += 1; all_match = False
+            elif np.allclose(m, r, rtol=1e-3, atol=1e-6):
+                c["match"] += 1
+            elif m[3] >= r[3] - 1e-6 * abs(r[3]) - 1e-9:
+                c["no_worse"] += 1; all_match = False
+            else:
+                c["worse"] += 1; all_match = False
+                c["worst"] = max(c["worst"], float(r[3] - m[3]))
+        if all_match:
+            r, m = ref[i, 16:21], got[i, 16:21]
+            if not (np.array_equal(np.isnan(r), np.isnan(m)) and np.allclose(m[~np.isnan(r)], r[~np.isnan(r)], rtol=2e-3, atol=1e-6)):
+                c["cross_bad"] += 1
+    return c

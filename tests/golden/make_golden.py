@@ -9,7 +9,9 @@ For each seeded synthetic set it imports the reference's own extractors from
 ``/root/reference/src/features`` (and exec's ``scripts/train_v55_powerlaw.py:106-202`` for the
 script-level decline-model fits), runs them on the long-format DataFrame, and stores
 inputs + outputs as ``<name>.npz``.  ``multiband_gp`` cannot be run (it imports ``george``,
-absent here) so it has no golden -- see ``oracle/gp2d.py``.
+absent here) so it has no golden -- see ``oracle/gp2d.py``.  The per-band GP module
+(``gaussian_process.py``, scikit-learn) runs and is recorded as ``gp1d_*``;
+``python tests/golden/make_golden.py --add gp1d`` adds it to existing fixtures without re-running the rest.
 
 Nothing is copied from the reference: only its outputs are recorded.
 """
@@ -89,8 +91,33 @@ def run_reference(table):
     return out
 
 
+def run_reference_gp1d(table):
+    """src/features/gaussian_process.py (sklearn GaussianProcessRegressor) -> gp1d_rows / gp1d_present."""
+    from features.gaussian_process import extract_gp_features
+    lc, meta, ids = table.to_frame(), table.metadata_frame(), list(table.object_ids)
+    with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        df = extract_gp_features(lc, meta, ids, verbose=False)
+    cols = [c for c in df.columns if c != "object_id"]
+    assert cols == schema.MODULE_COLUMNS["gp1d"] and df.columns[-1] == "object_id", cols
+    id_to_idx = {s: k for k, s in enumerate(ids)}
+    return {"gp1d_rows": df[cols].to_numpy(dtype=np.float64),
+            "gp1d_present": np.array([id_to_idx[s] for s in df["object_id"]], dtype=np.int64)}
+
+
+def add_gp1d(name, table):
+    """Append the gp1d golden to an existing fixture; the stored inputs must be the table's."""
+    path = os.path.join(HERE, f"{name}.npz")
+    old = dict(np.load(path))
+    assert np.array_equal(old["t"], table.t) and np.array_equal(old["flux"], table.flux) and np.array_equal(old["obj"], table.obj)
+    old.update(run_reference_gp1d(table))
+    np.savez_compressed(path, **old)
+    print(name, "gp1d added:", old["gp1d_rows"].shape, os.path.getsize(path) // 1024, "KiB")
+
+
 def save(name, table):
     ref = run_reference(table)
+    ref.update(run_reference_gp1d(table))
     path = os.path.join(HERE, f"{name}.npz")
     np.savez_compressed(path, obj=table.obj, band=table.band, t=table.t, flux=table.flux, err=table.err,
                         n_obj=np.int64(table.n_obj), z=table.z, ebv=table.ebv, **ref)
@@ -98,7 +125,10 @@ def save(name, table):
 
 
 if __name__ == "__main__":
-    save("ref_sparse", make_table(48, config_index=0))
-    save("ref_dense", make_table(24, seed=424242, count_scale=2.5))
-    save("ref_edge", make_edge_table())
-    save("ref_c1_256", make_table(256, config_index=1))      # a slice of the C1-shaped set: more objects, same generator
+    tables = [("ref_sparse", lambda: make_table(48, config_index=0)),
+              ("ref_dense", lambda: make_table(24, seed=424242, count_scale=2.5)),
+              ("ref_edge", make_edge_table),
+              ("ref_c1_256", lambda: make_table(256, config_index=1))]   # a slice of the C1-shaped set: more objects, same generator
+    only_gp1d = sys.argv[1:3] == ["--add", "gp1d"]
+    for name, make in tables:
+        (add_gp1d if only_gp1d else save)(name, make())

@@ -13,6 +13,8 @@
 #include "physics.cuh"
 #include "gp_host.hpp"
 #include "fits_thread.cuh"
+#include "gp1d.cuh"
+#include "lbfgsb_exact.cuh"
 
 using namespace mlrn;
 
@@ -30,6 +32,20 @@ static void hs_decline_one(const double* t, const double* f, int n, double k, do
   if (job.init(t, f, n, k, code)) { while ((code = job.step()) == TRF_RUNNING) {} }
   *out = job.finish(code);
   if (status) { status[0] = code; status[1] = (code == FIT_SKIPPED || code == FIT_BAD_INPUT) ? 0 : job.trf.nfev; }
+}
+
+typedef double (*hs_objective)(const double* x, double* g);
+template <class Opt>
+static void hs_drive(hs_objective fn, const double* x0, const double* lo, const double* hi, double* x_out, double* f_out, int* counts) {
+  Opt o; o.start(x0, lo, hi);
+  // SciPy's ScalarFunction does not re-evaluate (or count) a point equal to the previous one; gp1d_band does the same
+  double px[3] = {qnan(), qnan(), qnan()}, f = 0.0, g[3]; int evals = 0;
+  for (;;) {
+    if (!(px[0] == o.x[0] && px[1] == o.x[1] && px[2] == o.x[2])) { f = fn(o.x, g); ++evals; for (int i = 0; i < 3; ++i) px[i] = o.x[i]; }
+    if (!o.advance(f, g)) break;
+  }
+  for (int i = 0; i < 3; ++i) x_out[i] = o.x[i];
+  *f_out = o.f; counts[0] = o.nit; counts[1] = evals; counts[2] = o.why;
 }
 
 extern "C" {
@@ -111,6 +127,36 @@ int hs_gp2d(long long n_obj, const long long* seg_off, const double* t, const do
     ObjView v;
     stage_object(tm, seg_off, t, f, e, rank, o, s.t.data(), s.f.data(), s.e.data(), s.rank.data(), v);
     gphost::gp2d_row(v, out + o * 27, status ? status + o * 4 : nullptr);
+  }
+  return 0;
+}
+
+// The bounded optimisers driven by a caller-supplied objective (python callback), which isolates them from the
+// objective's rounding: which = 0 -> csrc/lbfgsb.cuh (the product: explicit 3 x 3 model), 1 -> lbfgsb_exact.cuh
+// (TEST-ONLY routine-by-routine restatement of the published compact-form code).
+int hs_lbfgsb3(int which, hs_objective fn, const double* x0, const double* lo, const double* hi, double* x_out, double* f_out, int* counts) {
+  if (which == 0) hs_drive<LbfgsB<3>>(fn, x0, lo, hi, x_out, f_out, counts);
+  else hs_drive<LbfgsBExact<3>>(fn, x0, lo, hi, x_out, f_out, counts);
+  return 0;
+}
+
+// per-band 1-D GP (gp1d.cuh / lbfgsb.cuh); status: per band {evaluations, iterations, winning start}
+int hs_gp1d(long long n_obj, const long long* seg_off, const double* t, const double* f, const double* e,
+            const unsigned short* rank, double* out, int* status) {
+  HostTeam tm;
+  const int bands[4] = {BG, BR, BI, BZ};
+  std::vector<double> scratch(gp1d_scratch_doubles(MAX_OBS));
+  LbfgsB<3> opt; double ctl[8];
+  for (long long o = 0; o < n_obj; ++o) {
+    Gp1dBandResult res[4];
+    for (int j = 0; j < 4; ++j) {
+      const long long lo = seg_off[o * N_SEG + bands[j]];
+      const int n = (int)(seg_off[o * N_SEG + bands[j] + 1] - lo);
+      Gp1dScratch s = gp1d_carve(scratch.data(), n);
+      gp1d_band(tm, t + lo, f + lo, e + lo, n, s, &opt, ctl, res[j]);
+      if (status) { status[o * 12 + 3 * j] = res[j].nfev; status[o * 12 + 3 * j + 1] = res[j].nit; status[o * 12 + 3 * j + 2] = res[j].winner; }
+    }
+    gp1d_tail(res, out + o * GP1D_COLS);
   }
   return 0;
 }

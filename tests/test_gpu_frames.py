@@ -42,6 +42,7 @@ CASES = [("statistical", "features.statistical", "extract_statistical_features",
          ("physics", "features.physics_based", "extract_physics_features", True),
          ("bazin", "features.bazin_fitting", "extract_bazin_features", False),
          ("gp2d", "features.multiband_gp", "extract_multiband_gp_features", True),
+         ("gp1d", "features.gaussian_process", "extract_gp_features", True),
          ("powerlaw", "features.powerlaw", "extract_powerlaw_features", False)]
 
 
@@ -88,3 +89,21 @@ def test_default_object_ids_and_metadata_merge(golden, features_pkg):
     np.testing.assert_allclose(full["luminosity_distance"], 4280 * z)
     np.testing.assert_allclose(full["time_dilation"], 1 + z)
     assert importlib.import_module("features").extract_statistical_features is st.extract_statistical_features
+
+
+def test_one_pack_pipeline_returns_the_per_module_frames(golden, features_pkg):
+    """features.pipeline.extract_feature_tables (one K1 pack, all nine passes) == the per-module extractors"""
+    g = golden["ref_sparse"]
+    lc, meta, ids = _frames(g)
+    pipe = importlib.import_module("features.pipeline")
+    request = list(ids[5:30])
+    tables = pipe.extract_feature_tables(lc, meta, request)
+    assert set(tables) == set(pipe.ALL_MODULES)
+    for module, modname, fn, needs_meta in CASES:
+        extract = getattr(importlib.import_module(modname), fn)
+        kw = {"verbose": False} if module in ("gp2d", "gp1d") else {}
+        df = extract(lc, meta, request, **kw) if needs_meta else extract(lc, request)
+        assert list(df.columns) == list(tables[module].columns)
+        assert df.equals(tables[module]), module          # same kernels on the same packed rows: bit-identical
+    with pytest.raises(KeyError):
+        pipe.extract_feature_tables(lc, meta, request, modules=["nope"])

@@ -13,7 +13,7 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 
-from fitparity import classify_bazin, classify_r2   # noqa: E402
+from fitparity import classify_bazin, classify_gp1d, classify_r2   # noqa: E402
 from packref import pack_reference                   # noqa: E402
 
 P = ctypes.c_void_p
@@ -95,3 +95,59 @@ def test_lbfgs4_and_tile_sweep_follow_scipy(hs):
             ok = ~np.isnan(row)
             assert np.array_equal(np.isnan(out[k]), np.isnan(row))
             np.testing.assert_allclose(out[k][ok], row[ok], rtol=1e-6, atol=1e-9)
+
+
+def test_lbfgsb_follows_scipy_on_the_same_objective(hs):
+    """lbfgsb.cuh driven through a callback with the oracle's own objective: isolates the optimiser from the
+    objective's rounding.  Iteration and evaluation counts must equal SciPy's on (nearly) every start."""
+    from scipy.optimize import minimize
+    from mallorn_astrophysics_b200.synth import make_table
+    from oracle import gp1d
+    from oracle.common import group_objects
+    CB = ctypes.CFUNCTYPE(ctypes.c_double, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double))
+    lo = np.ascontiguousarray(gp1d.LOG_BOUNDS[:, 0]); hi = np.ascontiguousarray(gp1d.LOG_BOUNDS[:, 1])
+    tb = make_table(10, config_index=1)
+    total = same = at_bound = 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for _, v in group_objects(tb.obj, tb.band, tb.t, tb.flux, tb.err, tb.n_obj):
+            for b in gp1d.BANDS:
+                p = gp1d.prepare(*v.band_sorted(b))
+                if p is None:
+                    continue
+                x, y, alpha = p[0], p[1], p[2]
+                d2 = (x[:, None] - x[None, :]) ** 2
+
+                def obj(xp, gp):
+                    fv, g = gp1d.neg_lml(np.array([xp[0], xp[1], xp[2]]), d2, y, alpha)
+                    gp[0], gp[1], gp[2] = g
+                    return float(fv)
+                cb = CB(obj)
+                for start in (gp1d.THETA0, *gp1d.RESTARTS):
+                    res = minimize(gp1d.neg_lml, start, args=(d2, y, alpha), method="L-BFGS-B", jac=True, bounds=gp1d.LOG_BOUNDS)
+                    xo = np.zeros(3); fo = ctypes.c_double(); cnt = np.zeros(3, np.int32)
+                    s0 = np.ascontiguousarray(start)
+                    hs.hs_lbfgsb3(cb, s0.ctypes.data_as(P), lo.ctypes.data_as(P), hi.ctypes.data_as(P), xo.ctypes.data_as(P),
+                                  ctypes.byref(fo), cnt.ctypes.data_as(P))
+                    total += 1
+                    same += (cnt[0] == res.nit and cnt[1] == res.nfev)
+                    at_bound += bool(np.any((res.x <= lo) | (res.x >= hi)))
+                    assert fo.value <= res.fun + 1e-6 * abs(res.fun) + 1e-9, (fo.value, res.fun)
+    assert total >= 120 and same >= 0.97 * total, (same, total)
+    assert at_bound >= 0.3 * total          # the bound logic (Cauchy point, projected subspace step) is really exercised
+
+
+@pytest.mark.parametrize("fixture", ["ref_sparse", "ref_edge"])
+def test_per_band_gp_templates_match_reference(golden, hs, fixture):
+    """gp1d.cuh (symmetric sweep + lbfgsb.cuh, four starts) host instantiation vs the reference's sklearn output."""
+    g = golden[fixture]
+    pk, n_obj = _pack(g)
+    out, st = _run(hs, "hs_gp1d", 21, pk, n_obj, status_cols=12)
+    pres, ref = g["gp1d_present"], g["gp1d_rows"]
+    keep = pres != (TIE_OBJECT if fixture == "ref_edge" else -1)
+    got, ref = out[pres][keep], ref[keep]
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    c = classify_gp1d(got, ref)                                    # tests/fitparity.py: the north star's fit rule
+    assert c["worse"] == 0 and c["nan_diff"] == 0 and c["cross_bad"] == 0 and c["match"] >= 0.98 * c["fits"], c
+    fitted = st[pres][keep][:, 2::3] >= 0
+    assert fitted.sum() > 50 and (st[pres][keep][:, 0::3][fitted] >= 4).all()

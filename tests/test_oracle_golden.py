@@ -38,6 +38,13 @@ def test_fit_modules_match_reference(golden, fixture, module):
     _check(golden[fixture], module, rtol=1e-12, skip_obj=(TIE_OBJECT,) if fixture == "ref_edge" else ())
 
 
+@pytest.mark.parametrize("fixture", ["ref_sparse", "ref_edge"])
+def test_per_band_gp_matches_reference(golden, fixture):
+    # numpy restatement of what sklearn's GaussianProcessRegressor does, same scipy L-BFGS-B: agrees to ~1e-9 in
+    # practice (LAPACK Cholesky vs cho_solve ordering); 1e-6 leaves room for a different BLAS
+    _check(golden[fixture], "gp1d", rtol=1e-6, skip_obj=(TIE_OBJECT,) if fixture == "ref_edge" else ())
+
+
 def test_absent_object_is_omitted(golden):
     g = golden["ref_edge"]
     assert 20 not in g["statistical_present"]            # object 20 has no rows (statistical.py:163-165)
