@@ -74,27 +74,50 @@ MLRN_FN bool gp1d_objective(const Team& tm, int n, const Gp1dScratch& s, const d
     A[wk.e] = val;
   }
   tm.sync();
+  // Sweep.  Lane = column: in row i the lanes j <= i update A(i, j) -= v_i w_j (consecutive addresses, v_i broadcast).
+  // Each step also deposits the next pivot column into the other buffer, so there is one barrier per pivot.
+  double* __restrict__ vc = v;
+  double* __restrict__ vn = w;
+  for (int i = tm.rank(); i < n1; i += Team::size) vc[i] = A[tri_size(i)];        // column 0
+  tm.sync();
   bool ok = true;
   for (int k = 0; k < n; ++k) {
-    const int rowk = tri_size(k);
-    const double pv = A[rowk + k];
+    const double pv = vc[k];
     if (!(pv > 0.0)) { ok = false; break; }
     const double ip = 1.0 / pv;
-    // v = column k of the current matrix (both halves of the symmetric storage), w = v / pivot
-    for (int i = tm.rank(); i < n1; i += Team::size) {
-      const double vi = (i <= k) ? A[rowk + i] : A[tri_size(i) + k];
-      v[i] = vi; w[i] = vi * ip;
-    }
     if (tm.rank() == 0) piv[k] = pv;
-    tm.sync();
-    for (wk.begin(tm.rank()); wk.e < total; wk.step(Team::size)) {
-      double val;
-      if (wk.j == k) val = (wk.i == k) ? -ip : w[wk.i];
-      else if (wk.i == k) val = w[wk.j];
-      else val = A[wk.e] - v[wk.i] * w[wk.j];
-      A[wk.e] = val;
+    const int kn = k + 1;
+    for (int jb = 0; jb < n1; jb += Team::size) {
+      const int j = jb + tm.rank();
+      if (j < n1) {
+        const double wj = vc[j] * ip;
+        const bool jn = (j == kn);
+        int e = tri_size(jb) + j, i = jb;
+        // rows above the pivot row: plain rank-1 update (the lane that owns column k writes values that the
+        // column pass below replaces)
+#pragma unroll 4
+        for (; i < k; ++i) { if (j <= i) A[e] = A[e] - vc[i] * wj; e += i + 1; }
+        if (i == k) { if (j <= i) A[e] = (j == k) ? -ip : wj; e += i + 1; ++i; }        // pivot row: w, and -1/pivot
+        if (i == kn && i < n1) {                                                      // next pivot row -> vn
+          if (j <= i) { const double r = A[e] - vc[i] * wj; A[e] = r; vn[j] = r; }
+          e += i + 1; ++i;
+        }
+#pragma unroll 4
+        for (; i < n1; ++i) {
+          if (j <= i) { const double r = A[e] - vc[i] * wj; A[e] = r; if (jn) vn[i] = r; }
+          e += i + 1;
+        }
+      }
     }
     tm.sync();
+    // pivot column below the diagonal: w_i (lane-parallel; also its entry in the next pivot column)
+    for (int i = kn + tm.rank(); i < n1; i += Team::size) {
+      const double r = vc[i] * ip;
+      A[tri_size(i) + k] = r;
+      if (i == kn) vn[k] = r;
+    }
+    tm.sync();
+    double* tmp = vc; vc = vn; vn = tmp;
   }
   if (!ok) { fval = pinf(); grad[0] = grad[1] = grad[2] = 0.0; tm.sync(); return false; }
   const double* __restrict__ a = A + tri_size(n);              // row n: K^-1 y

@@ -97,9 +97,12 @@ def test_lbfgs4_and_tile_sweep_follow_scipy(hs):
             np.testing.assert_allclose(out[k][ok], row[ok], rtol=1e-6, atol=1e-9)
 
 
-def test_lbfgsb_follows_scipy_on_the_same_objective(hs):
-    """lbfgsb.cuh driven through a callback with the oracle's own objective: isolates the optimiser from the
-    objective's rounding.  Iteration and evaluation counts must equal SciPy's on (nearly) every start."""
+@pytest.mark.parametrize("which", [0, 1], ids=["product_dense_model", "exact_compact_form"])
+def test_lbfgsb_follows_scipy_on_the_same_objective(hs, which):
+    """The bounded optimisers driven through a callback with the oracle's own objective, which isolates them from the
+    objective's rounding: csrc/lbfgsb.cuh (the product: explicit 3 x 3 quasi-Newton model) and the TEST-ONLY
+    routine-by-routine restatement of the published compact-form code (tests/hostsim/lbfgsb_exact.cuh).
+    Iteration and evaluation counts must equal SciPy's on (nearly) every start."""
     from scipy.optimize import minimize
     from mallorn_astrophysics_b200.synth import make_table
     from oracle import gp1d
@@ -127,7 +130,7 @@ def test_lbfgsb_follows_scipy_on_the_same_objective(hs):
                     res = minimize(gp1d.neg_lml, start, args=(d2, y, alpha), method="L-BFGS-B", jac=True, bounds=gp1d.LOG_BOUNDS)
                     xo = np.zeros(3); fo = ctypes.c_double(); cnt = np.zeros(3, np.int32)
                     s0 = np.ascontiguousarray(start)
-                    hs.hs_lbfgsb3(cb, s0.ctypes.data_as(P), lo.ctypes.data_as(P), hi.ctypes.data_as(P), xo.ctypes.data_as(P),
+                    hs.hs_lbfgsb3(ctypes.c_int(which), cb, s0.ctypes.data_as(P), lo.ctypes.data_as(P), hi.ctypes.data_as(P), xo.ctypes.data_as(P),
                                   ctypes.byref(fo), cnt.ctypes.data_as(P))
                     total += 1
                     same += (cnt[0] == res.nit and cnt[1] == res.nfev)
