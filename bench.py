@@ -368,6 +368,11 @@ def run_gpu_arm(args):
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{n_cpu} objects of the same generator (seed {SEED}), modules {','.join(modules)}, "
                              f"{secs:.1f} s on {cores} processes"}
+            if widened is not None:
+                n_w = min(n_cpu, 8 * cores)
+                rate_w, secs_w = cpu_rate(sample_cols, n_w, ["gp1d"], cores)
+                widened["gp1d"]["cpu_baseline"] = {"value": rate_w, "unit": UNIT, "cores": cores, "kind": "port",
+                                                   "sample": f"first {n_w} objects of the CPU sample, oracle/gp1d.py, {secs_w:.1f} s"}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -74,8 +74,9 @@ MLRN_FN bool gp1d_objective(const Team& tm, int n, const Gp1dScratch& s, const d
     A[wk.e] = val;
   }
   tm.sync();
-  // Sweep.  Lane = column: in row i the lanes j <= i update A(i, j) -= v_i w_j (consecutive addresses, v_i broadcast).
-  // Each step also deposits the next pivot column into the other buffer, so there is one barrier per pivot.
+  // Sweep.  Lane = column: in row i the lanes j <= i update A(i, j) -= v_i w_j (consecutive addresses, v_i broadcast,
+  // w_j in a register; predicated, no branches).  The lane that owns the pivot column computes throw-away values there;
+  // a short lane-parallel pass then writes that column (w_i) and collects the next pivot column.
   double* __restrict__ vc = v;
   double* __restrict__ vn = w;
   for (int i = tm.rank(); i < n1; i += Team::size) vc[i] = A[tri_size(i)];        // column 0
@@ -91,30 +92,19 @@ MLRN_FN bool gp1d_objective(const Team& tm, int n, const Gp1dScratch& s, const d
       const int j = jb + tm.rank();
       if (j < n1) {
         const double wj = vc[j] * ip;
-        const bool jn = (j == kn);
         int e = tri_size(jb) + j, i = jb;
-        // rows above the pivot row: plain rank-1 update (the lane that owns column k writes values that the
-        // column pass below replaces)
 #pragma unroll 4
         for (; i < k; ++i) { if (j <= i) A[e] = A[e] - vc[i] * wj; e += i + 1; }
         if (i == k) { if (j <= i) A[e] = (j == k) ? -ip : wj; e += i + 1; ++i; }        // pivot row: w, and -1/pivot
-        if (i == kn && i < n1) {                                                      // next pivot row -> vn
-          if (j <= i) { const double r = A[e] - vc[i] * wj; A[e] = r; vn[j] = r; }
-          e += i + 1; ++i;
-        }
 #pragma unroll 4
-        for (; i < n1; ++i) {
-          if (j <= i) { const double r = A[e] - vc[i] * wj; A[e] = r; if (jn) vn[i] = r; }
-          e += i + 1;
-        }
+        for (; i < n1; ++i) { if (j <= i) A[e] = A[e] - vc[i] * wj; e += i + 1; }
       }
     }
     tm.sync();
-    // pivot column below the diagonal: w_i (lane-parallel; also its entry in the next pivot column)
-    for (int i = kn + tm.rank(); i < n1; i += Team::size) {
-      const double r = vc[i] * ip;
-      A[tri_size(i) + k] = r;
-      if (i == kn) vn[k] = r;
+    for (int i = tm.rank(); i < n1; i += Team::size) {
+      if (i > k) A[tri_size(i) + k] = vc[i] * ip;                                     // pivot column below the diagonal: w_i
+      // next pivot column: row k+1 up to the diagonal, column k+1 below it; its entry in column k is the w just defined
+      vn[i] = (i == k) ? vc[kn] * ip : ((i <= kn) ? A[tri_size(kn) + i] : A[tri_size(i) + kn]);
     }
     tm.sync();
     double* tmp = vc; vc = vn; vn = tmp;

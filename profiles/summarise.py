@@ -3,6 +3,7 @@
 
     python profiles/summarise.py launches gpurun_out/launches.csv            # per-kernel time shares (library kernels)
     python profiles/summarise.py full gpurun_out/prof.ncu-rep [kernel-regex] # key metrics of a --set full capture
+    python profiles/summarise.py hot gpurun_out/prof.ncu-rep                 # where the instructions go (SASS page, 512-byte buckets)
 """
 import collections
 import csv
@@ -64,8 +65,40 @@ def full(path, pattern=None):
         print()
 
 
+def hot(path, bucket=0x200, top=24):
+    """Instruction and stall-sample shares per code-address bucket of the first kernel of a --set full capture
+    (needs --import-source on / -lineinfo only for the source column; the SASS page is always there)."""
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr = rows[1]
+    ia, ie, isamp, ith = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Avg. Threads Executed")
+    isrc = hdr.index("Source")
+    data, base = [], None
+    for r in rows[2:]:
+        try:
+            a = int(r[ia], 16)
+        except (ValueError, IndexError):
+            continue
+        base = a if base is None else base
+        data.append((a - base, r[isrc].strip(), int(r[ie]), int(r[isamp]), float(r[ith])))
+    tot, tots = sum(d[2] for d in data), sum(d[3] for d in data)
+    print(f"# {rows[0][1][:100]}")
+    print(f"# {len(data)} SASS instructions, {tot:.4g} warp instructions executed, {tots} stall samples")
+    agg = collections.OrderedDict()
+    for off, src, n, sm, th in data:
+        x = agg.setdefault(off // bucket, [0, 0, 0.0, collections.Counter()])
+        x[0] += n; x[1] += sm; x[2] += n * th
+        x[3][src.split()[0] if src else "?"] += n
+    print(f"{'code offset':>12s} {'instr %':>8s} {'samples %':>10s} {'avg threads':>12s}  dominant opcodes")
+    for k, (n, sm, th, ops) in sorted(sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]):
+        names = ", ".join(f"{o} {100 * c / max(n, 1):.0f}%" for o, c in ops.most_common(4))
+        print(f"{hex(k * bucket):>12s} {100 * n / tot:8.1f} {100 * sm / max(tots, 1):10.1f} {th / max(n, 1):12.1f}  {names}")
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2])
+    elif sys.argv[1] == "hot":
+        hot(sys.argv[2])
     else:
         full(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
