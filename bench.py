@@ -15,8 +15,9 @@ library exports (statistical, colors, shape, tde_physics, physics_based, bazin, 
              the step; ``passes`` lists every pass's share of the step.
 * ``cpu_baseline`` the CPU oracle (``oracle/``: the reference's numpy/scipy arithmetic) on a bounded
              sample of the same workload, all host cores.
-* ``widened``  SURVEY 8(f) rows built so far, timed beside the step on a slice of the same batch: the per-band
-             1-D GP pass (``extract_gp_features``, 21 columns); not part of ``value`` (the 434-column table).
+* ``widened``  SURVEY 8(f) rows built so far, measured beside the step and not part of ``value`` (the 434-column
+             table): the per-band 1-D GP pass (``extract_gp_features``, 21 columns) on a slice of the same batch, and
+             the native CSV ingest against the reference's pandas loading path on the box's host cores.
 * ``--impl reference`` times only that CPU path (the reference has no GPU path and, being a Python
              package with no native code, "the reference's own CPU implementation" is the oracle
              restatement: ``/root/reference`` does not exist on the GPU box).
@@ -135,6 +136,45 @@ def host_sample(n_objects):
     from mallorn_astrophysics_b200.synth import make_table
     tb = make_table(n_objects, seed=SEED)
     return {"obj": tb.obj, "band": tb.band, "t": tb.t, "flux": tb.flux, "err": tb.err, "z": tb.z}
+
+
+def ingest_rates(n_objects=2000):
+    """SURVEY 8(f) row 1 measured on this box's host cores: the reference's loading path (pd.read_csv of the split
+    files + concat, then the factorisation) against the native ingest (libmallorn_ingest.so) on the same files."""
+    import shutil
+    import tempfile
+    import pandas as pd
+    from mallorn_astrophysics_b200 import ingest
+    from mallorn_astrophysics_b200.store import frame_columns
+    from mallorn_astrophysics_b200.synth import make_table
+    root = tempfile.mkdtemp(prefix="mlrn_bench_ingest_")
+    try:
+        lc = make_table(n_objects, seed=SEED).to_frame()
+        edges = np.linspace(0, len(lc), 5).astype(int)
+        paths = []
+        for i in range(4):
+            d = os.path.join(root, f"split_{i + 1:02d}")
+            os.makedirs(d)
+            paths.append(os.path.join(d, "train_full_lightcurves.csv"))
+            lc.iloc[edges[i]:edges[i + 1]].to_csv(paths[-1], index=False)
+        size = sum(os.path.getsize(p) for p in paths)
+        t0 = time.perf_counter()
+        ref = frame_columns(pd.concat([pd.read_csv(p) for p in paths], ignore_index=True), None)
+        t_ref = time.perf_counter() - t0
+        ingest.read_lightcurve_csv(paths)                                   # warm (page cache, thread pool)
+        t0 = time.perf_counter()
+        got = ingest.read_lightcurve_csv(paths)
+        t_nat = time.perf_counter() - t0
+        same = bool(np.array_equal(got.obj, ref[0]) and np.array_equal(got.band, ref[1]) and
+                    all(np.array_equal(a.view(np.uint64), b.view(np.uint64))
+                        for a, b in ((got.t, ref[2]), (got.flux, ref[3]), (got.err, ref[4]))))
+        return {"reference": "load_lightcurves (data_loader.py:36-62) + groupby factorisation", "rows": int(len(lc)),
+                "csv_bytes": int(size), "pandas_mb_per_s": size / 1e6 / t_ref, "native_mb_per_s": size / 1e6 / t_nat,
+                "native_rows_per_s": len(lc) / t_nat, "threads": os.cpu_count(), "bit_identical_to_pandas": same}
+    except Exception as exc:                                                # never lose the bench line over the side measurement
+        return {"error": f"{type(exc).__name__}: {exc}"}
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
 
 
 def run_reference_arm(args):
@@ -373,6 +413,7 @@ def run_gpu_arm(args):
                 rate_w, secs_w = cpu_rate(sample_cols, n_w, ["gp1d"], cores)
                 widened["gp1d"]["cpu_baseline"] = {"value": rate_w, "unit": UNIT, "cores": cores, "kind": "port",
                                                    "sample": f"first {n_w} objects of the CPU sample, oracle/gp1d.py, {secs_w:.1f} s"}
+                widened["ingest"] = ingest_rates()
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

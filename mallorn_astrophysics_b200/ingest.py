@@ -1,0 +1,121 @@
+"""Host ingest of the reference's light-curve files without a DataFrame (``libmallorn_ingest.so``).
+
+``read_lightcurve_csv(paths)`` is the columnar counterpart of ``utils.data_loader.load_lightcurves``
+(``src/utils/data_loader.py:36-62``): the split files are memory-mapped and parsed by a pool of threads straight
+into the flat columns K1 takes (``obj`` int32 numbered by first appearance, ``band`` uint8, ``t / flux / err``
+float64, file order) plus the id table -- bit-identical to ``pd.concat([pd.read_csv(p) ...])`` followed by
+``store.frame_columns`` (``tests/test_ingest_csv.py``), at several times pandas' speed per core and on all cores.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Optional, Sequence, Union
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmallorn_ingest.so")
+_lib: Optional[C.CDLL] = None
+
+
+class MallornIngestError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MallornIngestError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(LIB_PATH)
+        vp = C.c_void_p
+        L.mlrn_ingest_last_error.restype = C.c_char_p
+        L.mlrn_ingest_csv.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_int, C.POINTER(vp)]
+        L.mlrn_table_rows.restype = C.c_int64
+        L.mlrn_table_objects.restype = C.c_int32
+        L.mlrn_table_id_bytes.restype = C.c_int64
+        for name in ("mlrn_table_obj", "mlrn_table_band", "mlrn_table_time", "mlrn_table_flux", "mlrn_table_err",
+                     "mlrn_table_id_offsets", "mlrn_table_id_chars"):
+            getattr(L, name).restype = vp
+        for name in ("mlrn_table_rows", "mlrn_table_objects", "mlrn_table_id_bytes", "mlrn_table_obj", "mlrn_table_band",
+                     "mlrn_table_time", "mlrn_table_flux", "mlrn_table_err", "mlrn_table_id_offsets", "mlrn_table_id_chars",
+                     "mlrn_table_free"):
+            getattr(L, name).argtypes = [vp]
+        L.mlrn_table_free.restype = None
+        _lib = L
+    return _lib
+
+
+@dataclass
+class LightCurveColumns:
+    """Flat long-format light curves in file order (the inputs of ``LightCurveStore``)."""
+    obj: np.ndarray          # int32 [rows], position in ``object_ids``; -1 = row without an id
+    band: np.ndarray         # uint8 [rows], 0..5 = u g r i z y, 6 = other
+    t: np.ndarray            # float64 [rows]
+    flux: np.ndarray
+    err: np.ndarray
+    object_ids: np.ndarray   # object [n_obj], order of first appearance (== DataFrame['object_id'].unique())
+
+    @property
+    def n_obj(self) -> int:
+        return len(self.object_ids)
+
+    @property
+    def n_rows(self) -> int:
+        return len(self.obj)
+
+    def to_frame(self):
+        """The reference's long DataFrame (for code that still wants one)."""
+        import pandas as pd
+        bands = np.array(["u", "g", "r", "i", "z", "y", None], dtype=object)
+        ids = np.append(self.object_ids, None)
+        return pd.DataFrame({"object_id": ids[self.obj], "Time (MJD)": self.t, "Flux": self.flux,
+                             "Flux_err": self.err, "Filter": bands[self.band]})
+
+
+def _copy(ptr, n, dtype):
+    if n == 0:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dtype))), shape=(n,)).copy()
+
+
+def read_lightcurve_csv(paths: Union[str, Path, Sequence[Union[str, Path]]], threads: int = 0) -> LightCurveColumns:
+    """Parse one or more light-curve CSV files as one concatenated table.  Structural problems (missing column,
+    ragged line, non-numeric field, unreadable file) raise ``MallornIngestError``."""
+    if isinstance(paths, (str, Path)):
+        paths = [paths]
+    L = lib()
+    enc = [os.fsencode(str(p)) for p in paths]
+    arr = (C.c_char_p * len(enc))(*enc)
+    h = C.c_void_p()
+    rc = L.mlrn_ingest_csv(arr, len(enc), int(threads), C.byref(h))
+    if rc != 0:
+        raise MallornIngestError(f"mlrn_ingest_csv failed (code {rc}): {L.mlrn_ingest_last_error().decode()}")
+    try:
+        n, k = L.mlrn_table_rows(h), L.mlrn_table_objects(h)
+        off = _copy(L.mlrn_table_id_offsets(h), k + 1, np.int64)
+        chars = C.string_at(L.mlrn_table_id_chars(h), L.mlrn_table_id_bytes(h)) if k else b""
+        ids = np.empty(k, dtype=object)
+        for i in range(k):
+            ids[i] = chars[off[i]:off[i + 1]].decode()
+        return LightCurveColumns(_copy(L.mlrn_table_obj(h), n, np.int32), _copy(L.mlrn_table_band(h), n, np.uint8),
+                                 _copy(L.mlrn_table_time(h), n, np.float64), _copy(L.mlrn_table_flux(h), n, np.float64),
+                                 _copy(L.mlrn_table_err(h), n, np.float64), ids)
+    finally:
+        L.mlrn_table_free(h)
+
+
+def load_lightcurves(split: str = "train", data_path: Union[str, Path, None] = None, threads: int = 0) -> LightCurveColumns:
+    """``utils.data_loader.load_lightcurves`` (data_loader.py:36-62) without the DataFrame: every existing
+    ``split_XX/{split}_full_lightcurves.csv`` for XX = 01..20, concatenated in that order."""
+    if data_path is None:
+        raise ValueError("data_path is required (the reference defaults to <its repo>/data/raw)")
+    data_path = Path(data_path)
+    files = [data_path / f"split_{i:02d}" / f"{split}_full_lightcurves.csv" for i in range(1, 21)]
+    files = [f for f in files if f.exists()]
+    if not files:
+        raise FileNotFoundError(f"No {split} lightcurve files found")
+    return read_lightcurve_csv(files, threads)

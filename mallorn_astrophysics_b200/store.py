@@ -100,6 +100,15 @@ class LightCurveStore:
         codes, band, t, flux, err, ids = frame_columns(lightcurves, object_ids)
         return cls(codes, band, t, flux, err, len(ids), device, stream), ids
 
+    @classmethod
+    def from_csv(cls, paths, device: int = 0, stream: int = 0, threads: int = 0):
+        """Light-curve CSV file(s) of the reference's layout -> packed store, without a DataFrame: the native host
+        ingest (``ingest.read_lightcurve_csv``: threads over memory-mapped chunks, pandas-exact number conversion)
+        feeds K1 directly.  Returns ``(store, ids)`` with ``ids`` in order of first appearance."""
+        from . import ingest
+        cols = ingest.read_lightcurve_csv(paths, threads)
+        return cls(cols.obj, cols.band, cols.t, cols.flux, cols.err, cols.n_obj, device, stream), cols.object_ids
+
     # ------------------------------------------------------------------ K1 outputs
     def segments(self) -> np.ndarray:
         """int32 [n_obj, 22]: per segment (count, file-order peak pos, time-order peak pos), peak_band."""

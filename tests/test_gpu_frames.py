@@ -107,3 +107,26 @@ def test_one_pack_pipeline_returns_the_per_module_frames(golden, features_pkg):
         assert df.equals(tables[module]), module          # same kernels on the same packed rows: bit-identical
     with pytest.raises(KeyError):
         pipe.extract_feature_tables(lc, meta, request, modules=["nope"])
+
+
+def test_store_from_csv_equals_store_from_the_pandas_frame(golden, tmp_path):
+    """files -> native ingest -> K1 (no DataFrame) gives the rows pd.read_csv -> from_frame gives, bit for bit"""
+    import pandas as pd
+    from mallorn_astrophysics_b200.store import LightCurveStore
+    g = golden["ref_sparse"]
+    lc, meta, ids = _frames(g)
+    lc = lc[lc["Filter"] != "X"]
+    paths = []
+    half = len(lc) // 2
+    for i, part in enumerate((lc.iloc[:half], lc.iloc[half:])):
+        p = tmp_path / f"part{i}.csv"
+        part.to_csv(p, index=False)
+        paths.append(p)
+    frame = pd.concat([pd.read_csv(p) for p in paths], ignore_index=True)
+    s1, ids1 = LightCurveStore.from_frame(frame)
+    s2, ids2 = LightCurveStore.from_csv(paths)
+    with s1, s2:
+        assert list(ids1) == list(ids2)
+        assert np.array_equal(s1.segments(), s2.segments())
+        for m in ("statistical", "bazin"):
+            assert np.array_equal(s1.features(m), s2.features(m), equal_nan=True), m

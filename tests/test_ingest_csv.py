@@ -1,0 +1,113 @@
+"""Native host ingest (libmallorn_ingest.so, csrc/ingest.cpp) against the reference's own loading path:
+``pd.read_csv`` of every split file + ``pd.concat`` (src/utils/data_loader.py:36-62), then the factorisation
+(store.frame_columns).  Bit-exact: ids and their order, dense object index, band codes, and every float -- which
+means reproducing pandas' default number converter, not a correctly rounded strtod."""
+import io
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import __graft_entry__ as entry
+from mallorn_astrophysics_b200.store import frame_columns
+
+
+@pytest.fixture(scope="module")
+def ingest():
+    entry.build()
+    from mallorn_astrophysics_b200 import ingest as ing
+    return ing
+
+
+def _write_splits(tmp_path, n_obj=300, seed=5, n_files=3, extra_column=True):
+    from mallorn_astrophysics_b200.synth import make_table
+    tb = make_table(n_obj, seed=seed)
+    lc = tb.to_frame()
+    rng = np.random.default_rng(seed)
+    lc.loc[rng.choice(len(lc), 40, replace=False), "Flux"] = np.nan          # empty fields
+    lc.loc[rng.choice(len(lc), 25, replace=False), "Filter"] = "w"           # a filter outside ugrizy
+    lc.loc[rng.choice(len(lc), 7, replace=False), "Flux_err"] = 0.0
+    lc.loc[rng.choice(len(lc), 5, replace=False), "Time (MJD)"] = 60000      # integer-looking values
+    if extra_column:
+        lc.insert(2, "detected", rng.integers(0, 2, len(lc)))
+    edges = np.linspace(0, len(lc), n_files + 1).astype(int)
+    paths = []
+    for i in range(n_files):
+        d = tmp_path / f"split_{i + 1:02d}"
+        d.mkdir()
+        p = d / "train_full_lightcurves.csv"
+        lc.iloc[edges[i]:edges[i + 1]].to_csv(p, index=False)
+        paths.append(p)
+    return paths
+
+
+def _reference_columns(paths):
+    lc = pd.concat([pd.read_csv(p) for p in paths], ignore_index=True)       # data_loader.py:53-62
+    return frame_columns(lc, None), lc
+
+
+def test_csv_ingest_is_bit_identical_to_the_pandas_path(ingest, tmp_path):
+    paths = _write_splits(tmp_path)
+    (obj, band, t, f, e, ids), lc = _reference_columns(paths)
+    for threads in (1, 4):
+        got = ingest.read_lightcurve_csv(paths, threads=threads)
+        assert list(got.object_ids) == list(ids)
+        assert np.array_equal(got.obj, obj) and np.array_equal(got.band, band)
+        for a, b in ((got.t, t), (got.flux, f), (got.err, e)):
+            assert a.dtype == np.float64 and np.array_equal(a.view(np.uint64), b.view(np.uint64))
+    via_loader = ingest.load_lightcurves("train", tmp_path)
+    assert np.array_equal(via_loader.obj, obj) and via_loader.n_obj == len(ids)
+    back = via_loader.to_frame()
+    assert np.array_equal(back["Flux"].to_numpy(), lc["Flux"].to_numpy(), equal_nan=True)
+    assert list(back["object_id"]) == list(lc["object_id"])
+
+
+def test_number_conversion_follows_pandas_not_strtod(ingest, tmp_path):
+    """random decimal spellings, including 17-digit reprs where pandas' converter is off by an ulp from strtod"""
+    rng = np.random.default_rng(11)
+    vals = np.concatenate([rng.normal(0, 5, 20000), 60000 + rng.uniform(0, 3000, 20000), rng.uniform(0, 1, 5000) * 10.0 ** rng.integers(-30, 30, 5000)])
+    texts = [repr(float(v)) for v in vals]
+    texts += ["%.3f" % v for v in vals[:5000]] + ["%.10e" % v for v in vals[:5000]] + ["%d" % int(v) for v in vals[20000:21000]]
+    texts += ["0.30000000000000004", "3.141592653589793238462643383279", "1e23", "-.5", "5.", "+7.25", "1E5", "4.9e-324", "1e-400",
+              "1e400", "123456789012345678901234567890.5", "0.000000000000000000000000123456789012345678", "inf", "-inf", "nan", "NA", ""]
+    p = tmp_path / "numbers.csv"
+    with open(p, "w") as fh:
+        fh.write("object_id,Time (MJD),Flux,Flux_err,Filter\n")
+        for s in texts:
+            fh.write(f"a,1.5,{s},1.0,g\n")
+    want = pd.read_csv(p)["Flux"].to_numpy(dtype=np.float64)
+    got = ingest.read_lightcurve_csv(p).flux
+    assert len(got) == len(texts)
+    same = (got.view(np.uint64) == want.view(np.uint64)) | (np.isnan(got) & np.isnan(want))
+    assert same.all(), [(texts[i], got[i], want[i]) for i in np.flatnonzero(~same)[:5]]
+    off = sum(float(s) != w for s, w in zip(texts[:45000], want[:45000]))
+    assert off > 0        # the reference's numbers are not the correctly rounded ones: this is why strtod would not do
+
+
+def test_structural_errors_raise(ingest, tmp_path):
+    p = tmp_path / "bad.csv"
+    p.write_text("object_id,Time (MJD),Flux,Filter\nx,1,2,g\n")
+    with pytest.raises(ingest.MallornIngestError, match="header"):
+        ingest.read_lightcurve_csv(p)
+    p.write_text("object_id,Time (MJD),Flux,Flux_err,Filter\nx,1,2,3\n")
+    with pytest.raises(ingest.MallornIngestError, match="fields"):
+        ingest.read_lightcurve_csv(p)
+    p.write_text("object_id,Time (MJD),Flux,Flux_err,Filter\nx,1,abc,3,g\n")
+    with pytest.raises(ingest.MallornIngestError, match="number"):
+        ingest.read_lightcurve_csv(p)
+    with pytest.raises(ingest.MallornIngestError, match="cannot open"):
+        ingest.read_lightcurve_csv(tmp_path / "missing.csv")
+    with pytest.raises(FileNotFoundError):
+        ingest.load_lightcurves("test", tmp_path)
+
+
+def test_header_order_crlf_and_missing_ids(ingest, tmp_path):
+    p = tmp_path / "crlf.csv"
+    p.write_bytes(b"Filter,Flux_err,Flux,Time (MJD),object_id\r\ng,0.5,1.25,60000.5,B\r\n\r\nr,0.25,-2.5,60001.5,\r\nz,1,3,60002,A\r\nq,1,3,60003,B")
+    got = ingest.read_lightcurve_csv(p)
+    want = frame_columns(pd.read_csv(p), None)
+    assert list(got.object_ids) == list(want[5]) == ["B", "A"]
+    assert np.array_equal(got.obj, want[0]) and got.obj.tolist() == [0, -1, 1, 0]
+    assert np.array_equal(got.band, want[1]) and got.band.tolist() == [1, 2, 4, 6]
+    assert np.array_equal(got.t, want[2]) and np.array_equal(got.flux, want[3]) and np.array_equal(got.err, want[4])
