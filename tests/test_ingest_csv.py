@@ -111,3 +111,13 @@ def test_header_order_crlf_and_missing_ids(ingest, tmp_path):
     assert np.array_equal(got.obj, want[0]) and got.obj.tolist() == [0, -1, 1, 0]
     assert np.array_equal(got.band, want[1]) and got.band.tolist() == [1, 2, 4, 6]
     assert np.array_equal(got.t, want[2]) and np.array_equal(got.flux, want[3]) and np.array_equal(got.err, want[4])
+
+
+def test_ingest_header_symbols_are_exported(ingest):
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "mallorn_ingest.h")).read()
+    names = sorted(set(re.findall(r"\b(mlrn_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 12
+    L = ingest.lib()
+    assert not [n for n in names if not hasattr(L, n)]
