@@ -115,6 +115,49 @@ def add_gp1d(name, table):
     print(name, "gp1d added:", old["gp1d_rows"].shape, os.path.getsize(path) // 1024, "KiB")
 
 
+def crafted_gp1d_cases():
+    """Ten hand-made objects for the per-band GP: constant flux, one epoch only, NaN rows leaving < 5 / >= 5 valid
+    points, zero and negative errors, duplicated times, exactly five points, huge and tiny errors, two clusters."""
+    rng = np.random.default_rng(1)
+    rows = []
+
+    def add(o, band, t, f, e):
+        rows.extend(zip([o] * len(t), [band] * len(t), t, f, e))
+    t = np.sort(60000 + rng.uniform(0, 500, 12))
+    add(0, 1, t, np.full(12, 3.0), np.full(12, 0.5))
+    add(1, 2, np.full(8, 60010.0), rng.normal(0, 1, 8), np.full(8, 0.3))
+    f = rng.normal(5, 2, 8); f[:4] = np.nan; add(2, 3, t[:8], f, np.full(8, 0.4))
+    f = rng.normal(5, 2, 12); f[[1, 5]] = np.nan; add(3, 1, t, f, np.full(12, 0.4))
+    e = np.full(12, 0.5); e[[0, 3]] = 0.0; e[7] = -1.0; add(4, 2, t, rng.normal(2, 3, 12), e)
+    tt = t.copy(); tt[3] = tt[2]; tt[9] = tt[8]; add(5, 3, tt, rng.normal(2, 3, 12), np.full(12, 0.6))
+    add(6, 4, t[:5], rng.normal(1, 1, 5), np.full(5, 0.2))
+    add(7, 1, t, rng.normal(0, 1, 12), np.full(12, 50.0))
+    add(8, 2, t, np.sin(t / 50) * 5, np.full(12, 1e-7))
+    tc = np.sort(np.concatenate([60000 + rng.uniform(0, 5, 10), 60400 + rng.uniform(0, 5, 10)]))
+    add(9, 3, tc, rng.normal(0, 2, 20), np.full(20, 0.5))
+    a = np.array(rows)
+    return (a[:, 0].astype(np.int32), a[:, 1].astype(np.uint8), a[:, 2].copy(), a[:, 3].copy(), a[:, 4].copy(), 10)
+
+
+def save_gp1d_crafted():
+    """gp1d_crafted.npz: the reference's extract_gp_features_single on the crafted objects (row per object)."""
+    import pandas as pd
+    from features.gaussian_process import extract_gp_features_single
+    obj, band, t, f, e, n_obj = crafted_gp1d_cases()
+    names = np.array(list("ugrizy"))
+    out = np.full((n_obj, 21), np.nan)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for k in range(n_obj):
+            m = obj == k
+            df = pd.DataFrame({"Time (MJD)": t[m], "Flux": f[m], "Flux_err": e[m], "Filter": names[band[m]]})
+            r = extract_gp_features_single(df)
+            out[k] = [r[c] for c in schema.MODULE_COLUMNS["gp1d"]]
+    path = os.path.join(HERE, "gp1d_crafted.npz")
+    np.savez_compressed(path, obj=obj, band=band, t=t, flux=f, err=e, n_obj=np.int64(n_obj), gp1d_rows=out)
+    print("gp1d_crafted", out.shape, "->", path)
+
+
 def save(name, table):
     ref = run_reference(table)
     ref.update(run_reference_gp1d(table))
@@ -130,5 +173,9 @@ if __name__ == "__main__":
               ("ref_edge", make_edge_table),
               ("ref_c1_256", lambda: make_table(256, config_index=1))]   # a slice of the C1-shaped set: more objects, same generator
     only_gp1d = sys.argv[1:3] == ["--add", "gp1d"]
+    if sys.argv[1:3] == ["--add", "gp1d_crafted"]:
+        save_gp1d_crafted()
+        sys.exit(0)
     for name, make in tables:
         (add_gp1d if only_gp1d else save)(name, make())
+    save_gp1d_crafted()

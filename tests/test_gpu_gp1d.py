@@ -103,3 +103,15 @@ def test_gp1d_is_deterministic_and_batch_independent():
     with LightCurveStore(sub.obj[keep], sub.band[keep], sub.t[keep], sub.flux[keep], sub.err[keep], 100) as s:
         c = s.features("gp1d")
     assert np.array_equal(c, a[:100], equal_nan=True)
+
+
+def test_gp1d_crafted_edge_cases():
+    """constant flux, a single epoch, NaN rows, non-positive errors, duplicated times, exactly five points, huge / tiny
+    errors -- against the reference's own output (tests/golden/gp1d_crafted.npz, made by make_golden.py)"""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gp1d_crafted.npz"))
+    rows, st = _gpu(g)
+    ref = g["gp1d_rows"]
+    assert np.array_equal(np.isnan(rows), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    np.testing.assert_allclose(rows[ok], ref[ok], rtol=1e-3, atol=1e-6)
+    assert (st[1] == [0, 0, -1] * 4).all() and st[0, 2] >= 0          # no fit for the single-epoch object; g band of object 0 fitted

@@ -154,3 +154,21 @@ def test_per_band_gp_templates_match_reference(golden, hs, fixture):
     assert c["worse"] == 0 and c["nan_diff"] == 0 and c["cross_bad"] == 0 and c["match"] >= 0.98 * c["fits"], c
     fitted = st[pres][keep][:, 2::3] >= 0
     assert fitted.sum() > 50 and (st[pres][keep][:, 0::3][fitted] >= 4).all()
+
+
+def test_per_band_gp_crafted_edge_cases(hs):
+    """constant flux, a single epoch, NaN rows, non-positive errors, duplicated times, exactly five points, huge / tiny
+    errors: host instantiation and oracle vs the reference's own output (tests/golden/gp1d_crafted.npz)"""
+    from oracle.extract import run_module
+    g = np.load(os.path.join(HERE, "golden", "gp1d_crafted.npz"))
+    pk, n_obj = _pack(g)
+    out, st = _run(hs, "hs_gp1d", 21, pk, n_obj, status_cols=12)
+    ref = g["gp1d_rows"]
+    assert np.array_equal(np.isnan(out), np.isnan(ref))
+    assert np.isnan(ref[1]).all() and np.isnan(ref[2]).all() and np.isfinite(ref[0, 0:4]).all()
+    ok = ~np.isnan(ref)
+    np.testing.assert_allclose(out[ok], ref[ok], rtol=1e-5, atol=1e-9)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _, rows = run_module("gp1d", g["obj"], g["band"], g["t"], g["flux"], g["err"], n_obj)
+    np.testing.assert_allclose(rows[ok], ref[ok], rtol=1e-5, atol=1e-9)
