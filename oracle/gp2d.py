@@ -22,6 +22,10 @@ options={'maxiter': 100})`` (multiband_gp.py:158-164).  The reference then reads
 parameter-vector positions 0, 1, 2 under the names amplitude / time metric / wave metric
 (:171-188); ``FEATURE_SLOTS`` keeps that positional mapping in one place.
 
+The mathematics of this file (likelihood, gradient, predictive mean) is cross-checked against scikit-learn's
+independent implementation of the same model in ``tests/test_gp2d_math_crosscheck.py``; the assumption that
+remains is george's parameter order and amplitude convention (items 2 and 4).
+
 Row layout is ``schema.GP2D_COLUMNS`` (27 values).
 """
 from __future__ import annotations
