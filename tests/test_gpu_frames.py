@@ -130,3 +130,24 @@ def test_store_from_csv_equals_store_from_the_pandas_frame(golden, tmp_path):
         assert np.array_equal(s1.segments(), s2.segments())
         for m in ("statistical", "bazin"):
             assert np.array_equal(s1.features(m), s2.features(m), equal_nan=True), m
+
+
+def test_cache_driver_writes_what_the_trainers_read(golden, features_pkg, tmp_path):
+    """features.caches.write_feature_caches on the GPU: every file loads with the reference's structure and holds the
+    frames the per-module extractors return"""
+    import pandas as pd
+    g = golden["ref_sparse"]
+    lc, meta, ids = _frames(g)
+    train_meta, test_meta = meta.iloc[:30].reset_index(drop=True), meta.iloc[30:].reset_index(drop=True)
+    train_lc = lc[lc["object_id"].isin(set(train_meta["object_id"]))]
+    test_lc = lc[lc["object_id"].isin(set(test_meta["object_id"]))]
+    caches = importlib.import_module("features.caches")
+    written = caches.write_feature_caches(train_lc, train_meta, test_lc, test_meta, tmp_path)
+    assert set(written) == set(caches.CACHE_FILES)
+    bz = pd.read_pickle(tmp_path / "bazin_features_cache.pkl")
+    direct = importlib.import_module("features.bazin_fitting").extract_bazin_features(test_lc, test_meta["object_id"].tolist())
+    assert direct.equals(bz["test"])
+    v4 = pd.read_pickle(tmp_path / "features_v4_cache.pkl")["train_features"]
+    assert len(v4) == 30 and v4.columns[0] == "object_id" and "luminosity_distance" in v4.columns and "stetson_j_gr" in v4.columns
+    assert len(pd.read_pickle(tmp_path / "powerlaw_features.pkl")) == 30
+    assert caches.write_feature_caches(train_lc, train_meta, test_lc, test_meta, tmp_path) == {}      # present -> untouched
