@@ -135,15 +135,12 @@ MLRN_FN bool gp1d_objective(const Team& tm, int n, const Gp1dScratch& s, const d
 
 struct Gp1dBandResult { double length_scale, amplitude, noise, loglik; int nfev, nit, winner; };
 
-// One band: validity mask, scaling, four optimiser runs, the reference's four numbers (gaussian_process.py:29-146).
-// gt/gf/ge: the band's time-sorted segment (n_raw rows, global memory); opt: one optimiser state owned by rank 0;
-// ctl: 8 doubles of team-visible scratch.
+// Band preparation (gaussian_process.py:54-85): validity mask, time scaling to [0, 1], flux standardisation, alpha.
+// gt/gf/ge: the band's time-sorted segment (n_raw rows, global memory).  Fills x, y, al [n]; returns n (0 = no fit).
 template <class Team>
-MLRN_FN void gp1d_band(const Team& tm, const double* gt, const double* gf, const double* ge, int n_raw,
-                       const Gp1dScratch& s, LbfgsB<3>* opt, double* ctl, Gp1dBandResult& out) {
-  out.length_scale = out.amplitude = out.noise = out.loglik = qnan();
-  out.nfev = 0; out.nit = 0; out.winner = -1;
-  if (n_raw < 5) return;
+MLRN_FN int gp1d_prepare(const Team& tm, const double* gt, const double* gf, const double* ge, int n_raw,
+                         double* sx, double* sy, double* sal, double& t_range, double& f_std) {
+  if (n_raw < 5) return 0;
   // keep rows with finite flux, finite error, error > 0 (:58); order preserved
   int n = 0;
   for (int base = 0; base < n_raw; base += Team::size) {
@@ -151,23 +148,32 @@ MLRN_FN void gp1d_band(const Team& tm, const double* gt, const double* gf, const
     double tt = 0.0, ff = 0.0, ee = 0.0; bool keep = false;
     if (i < n_raw) { tt = gt[i]; ff = gf[i]; ee = ge[i]; keep = !(is_nan(ff) || is_nan(ee) || ee <= 0.0); }
     const int slot = tm.compact_slot(keep, n);
-    if (keep) { s.x[slot] = tt; s.y[slot] = ff; s.al[slot] = ee; }
+    if (keep) { sx[slot] = tt; sy[slot] = ff; sal[slot] = ee; }
   }
   tm.sync();
-  if (n < 5) return;
-  const double t_min = team_min(tm, s.x, n), t_max = team_max(tm, s.x, n);
-  const double t_range = t_max - t_min;
-  if (t_range == 0.0 || is_nan(t_range)) return;
-  const double f_mean = team_mean(tm, s.y, n);
-  double f_std = sqrt(team_var(tm, s.y, n, f_mean));
+  if (n < 5) return 0;
+  const double t_min = team_min(tm, sx, n), t_max = team_max(tm, sx, n);
+  t_range = t_max - t_min;
+  if (t_range == 0.0 || is_nan(t_range)) return 0;
+  const double f_mean = team_mean(tm, sy, n);
+  f_std = sqrt(team_var(tm, sy, n, f_mean));
   if (f_std == 0.0) f_std = 1.0;
   for (int i = tm.rank(); i < n; i += Team::size) {
-    s.x[i] = (s.x[i] - t_min) / t_range;
-    s.y[i] = (s.y[i] - f_mean) / f_std;
-    const double en = s.al[i] / f_std;
-    s.al[i] = fmax(en * en, 1e-10);
+    sx[i] = (sx[i] - t_min) / t_range;
+    sy[i] = (sy[i] - f_mean) / f_std;
+    const double en = sal[i] / f_std;
+    sal[i] = fmax(en * en, 1e-10);
   }
   tm.sync();
+  return n;
+}
+
+// The four optimiser runs of one prepared band and the reference's four numbers (gaussian_process.py:88-146).
+// objective(theta, f, g): -ln L and its gradient, identical on every member; opt: optimiser state owned by rank 0;
+// ctl: 8 doubles of team-visible scratch.
+template <class Team, class Objective>
+MLRN_FN void gp1d_optimise(const Team& tm, Objective&& objective, double t_range, double f_std, LbfgsB<3>* opt, double* ctl,
+                           Gp1dBandResult& out) {
   const double LO[3] = {-4.605170185988091, -4.605170185988091, -11.512925464970229};      // ln 0.01, ln 0.01, ln 1e-5
   const double HI[3] = {4.605170185988092, 0.6931471805599453, 2.302585092994046};         // ln 100, ln 2, ln 10
   const double START[GP1D_STARTS][3] = {
@@ -186,7 +192,7 @@ MLRN_FN void gp1d_band(const Team& tm, const double* gt, const double* gf, const
     for (;;) {
       const double theta[3] = {ctl[0], ctl[1], ctl[2]};
       if (!(theta[0] == prev[0] && theta[1] == prev[1] && theta[2] == prev[2])) {
-        gp1d_objective(tm, n, s, theta, fv, g);
+        objective(theta, fv, g);
         ++evals;
         prev[0] = theta[0]; prev[1] = theta[1]; prev[2] = theta[2];
       }
@@ -212,6 +218,23 @@ MLRN_FN void gp1d_band(const Team& tm, const double* gt, const double* gf, const
   out.amplitude = sqrt(exp(best_x[0])) * f_std;
   out.noise = sqrt(exp(best_x[2])) * f_std;
   out.loglik = -best_f;
+}
+
+MLRN_FN void gp1d_clear(Gp1dBandResult& out) {
+  out.length_scale = out.amplitude = out.noise = out.loglik = qnan();
+  out.nfev = 0; out.nit = 0; out.winner = -1;
+}
+
+// One band with the packed-triangle sweep in team scratch `s` (gaussian_process.py:29-146).
+template <class Team>
+MLRN_FN void gp1d_band(const Team& tm, const double* gt, const double* gf, const double* ge, int n_raw,
+                       const Gp1dScratch& s, LbfgsB<3>* opt, double* ctl, Gp1dBandResult& out) {
+  gp1d_clear(out);
+  double t_range = 0.0, f_std = 1.0;
+  const int n = gp1d_prepare(tm, gt, gf, ge, n_raw, s.x, s.y, s.al, t_range, f_std);
+  if (n == 0) return;
+  gp1d_optimise(tm, [&](const double* theta, double& fv, double* g) { gp1d_objective(tm, n, s, theta, fv, g); },
+                t_range, f_std, opt, ctl, out);
 }
 
 // Cross-band block of extract_gp_features_single (gaussian_process.py:214-246); scalar, every member computes it.
