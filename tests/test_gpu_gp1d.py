@@ -115,3 +115,19 @@ def test_gp1d_crafted_edge_cases():
     ok = ~np.isnan(ref)
     np.testing.assert_allclose(rows[ok], ref[ok], rtol=1e-3, atol=1e-6)
     assert (st[1] == [0, 0, -1] * 4).all() and st[0, 2] >= 0          # no fit for the single-epoch object; g band of object 0 fitted
+
+
+@pytest.mark.skipif(os.environ.get("MLRN_TEST_EXPERIMENTAL") != "1",
+                    reason="register-tiled kernel (MLRN_GP1D_TILED=1) has only been validated by lane emulation on the CPU so far; "
+                           "set MLRN_TEST_EXPERIMENTAL=1 to run it on the GPU")
+def test_gp1d_register_tiled_kernel_matches_default(monkeypatch, golden):
+    g = golden["ref_c1_256"]
+    base, st = _gpu(g)
+    monkeypatch.setenv("MLRN_GP1D_TILED", "1")
+    tiled, st2 = _gpu(g)
+    monkeypatch.delenv("MLRN_GP1D_TILED")
+    pres, ref = g["gp1d_present"], g["gp1d_rows"]
+    _compare(tiled[pres], ref)
+    ok = ~np.isnan(base)
+    assert np.array_equal(np.isnan(tiled), np.isnan(base))
+    np.testing.assert_allclose(tiled[ok], base[ok], rtol=1e-4, atol=1e-8)
