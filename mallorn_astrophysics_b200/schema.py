@@ -106,11 +106,25 @@ GP1D_COLUMNS = (
     + ["gp_ls_ratio_gr", "gp_ls_ratio_ri", "gp_mean_length_scale", "gp_std_length_scale", "gp_mean_amplitude"]
 )
 
+RESEARCH_POWERLAW_NAMES = ["powerlaw_alpha", "powerlaw_alpha_deviation_53", "powerlaw_alpha_deviation_512", "powerlaw_chi2",
+                           "powerlaw_residual_std", "powerlaw_fit_success"]            # research_features.py:59-66
+RESEARCH_COLUMNS = (
+    [f"{b}_{s}" for b in "gri" for s in RESEARCH_POWERLAW_NAMES]
+    + ["optical_mean_powerlaw_alpha", "optical_std_powerlaw_alpha", "optical_mean_deviation_53"]
+    + ["nuclear_smoothness", "nuclear_concentration", "nuclear_variability_ratio", "nuclear_position_score"]
+    + ["g_r_color_at_peak", "g_r_color_peak_to_late", "r_i_color_at_peak", "r_i_color_peak_to_late"]
+    + ["mhps_10d", "mhps_30d", "mhps_100d", "mhps_10_100_ratio", "mhps_30_100_ratio", "mhps_dominant_scale"]
+    + ["luminosity_distance_mpc", "peak_luminosity", "luminosity_amplitude", "mean_luminosity", "luminosity_decline_rate"]
+)
+
 MODULE_COLUMNS = {
     "statistical": STAT_COLUMNS, "colors": COLOR_COLUMNS, "shape": SHAPE_COLUMNS,
     "tde": TDE_COLUMNS, "physics": PHYSICS_COLUMNS, "bazin": BAZIN_COLUMNS,
     "powerlaw": POWERLAW_COLUMNS, "gp2d": GP2D_COLUMNS, "gp1d": GP1D_COLUMNS,
 }
+# SURVEY 8(f) row 3, oracle stage only (no CUDA pass yet): not part of MODULE_COLUMNS / the C-ABI
+ORACLE_ONLY_COLUMNS = {"research": RESEARCH_COLUMNS}
+assert len(RESEARCH_COLUMNS) == 40
 
 assert len(STAT_COLUMNS) == 123 and len(COLOR_COLUMNS) == 83 and len(SHAPE_COLUMNS) == 65
 assert len(TDE_COLUMNS) == 25 and len(PHYSICS_COLUMNS) == 32 and len(BAZIN_COLUMNS) == 52

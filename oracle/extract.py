@@ -11,12 +11,12 @@ from typing import Optional, Tuple
 
 import numpy as np
 
-from . import bazin, colors, gp1d, gp2d, physics, powerlaw, shape, statistical, tde
+from . import bazin, colors, gp1d, gp2d, research, physics, powerlaw, shape, statistical, tde
 from .common import group_objects
 
 MODULES = ("statistical", "colors", "shape", "tde", "physics", "bazin", "powerlaw", "gp2d", "gp1d")
 _WIDTH = {"statistical": 123, "colors": 83, "shape": 65, "tde": 25, "physics": 32,
-          "bazin": 52, "powerlaw": 27, "gp2d": 27, "gp1d": 21, "segments": 22}
+          "bazin": 52, "powerlaw": 27, "gp2d": 27, "gp1d": 21, "research": 40, "segments": 22}
 
 
 def run_module(name: str, obj, band, t, f, e, n_obj: int,
@@ -44,6 +44,8 @@ def run_module(name: str, obj, band, t, f, e, n_obj: int,
             r = gp2d.object_row(v)
         elif name == "gp1d":
             r = gp1d.object_row(v)
+        elif name == "research":
+            r = research.object_row(v, float("nan") if z is None else float(z[k]))
         else:
             raise KeyError(name)
         present.append(k)
@@ -56,5 +58,5 @@ def run_module(name: str, obj, band, t, f, e, n_obj: int,
 
 def run_table(name: str, table, z_from_table: bool = True):
     """Convenience wrapper for a ``mallorn_astrophysics_b200.synth.LightCurveTable``-like object."""
-    z = table.z if (name == "physics" and z_from_table) else None
+    z = table.z if (name in ("physics", "research") and z_from_table) else None
     return run_module(name, table.obj, table.band, table.t, table.flux, table.err, table.n_obj, z)

@@ -105,6 +105,29 @@ def run_reference_gp1d(table):
             "gp1d_present": np.array([id_to_idx[s] for s in df["object_id"]], dtype=np.int64)}
 
 
+def run_reference_research(table):
+    """src/features/research_features.py (v115c block) -> research_rows / research_present."""
+    from features.research_features import extract_research_features
+    lc, meta, ids = table.to_frame(), table.metadata_frame(), list(table.object_ids)
+    with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        df = extract_research_features(lc, ids, meta, verbose=False)
+    cols = [c for c in df.columns if c != "object_id"]
+    assert cols == schema.RESEARCH_COLUMNS and df.columns[-1] == "object_id", cols
+    id_to_idx = {s: k for k, s in enumerate(ids)}
+    return {"research_rows": df[cols].to_numpy(dtype=np.float64),
+            "research_present": np.array([id_to_idx[s] for s in df["object_id"]], dtype=np.int64)}
+
+
+def add_module(name, table, runner, label):
+    path = os.path.join(HERE, f"{name}.npz")
+    old = dict(np.load(path))
+    assert np.array_equal(old["t"], table.t) and np.array_equal(old["flux"], table.flux) and np.array_equal(old["obj"], table.obj)
+    old.update(runner(table))
+    np.savez_compressed(path, **old)
+    print(name, label, "added:", os.path.getsize(path) // 1024, "KiB")
+
+
 def add_gp1d(name, table):
     """Append the gp1d golden to an existing fixture; the stored inputs must be the table's."""
     path = os.path.join(HERE, f"{name}.npz")
@@ -161,6 +184,7 @@ def save_gp1d_crafted():
 def save(name, table):
     ref = run_reference(table)
     ref.update(run_reference_gp1d(table))
+    ref.update(run_reference_research(table))
     path = os.path.join(HERE, f"{name}.npz")
     np.savez_compressed(path, obj=table.obj, band=table.band, t=table.t, flux=table.flux, err=table.err,
                         n_obj=np.int64(table.n_obj), z=table.z, ebv=table.ebv, **ref)
@@ -175,6 +199,10 @@ if __name__ == "__main__":
     only_gp1d = sys.argv[1:3] == ["--add", "gp1d"]
     if sys.argv[1:3] == ["--add", "gp1d_crafted"]:
         save_gp1d_crafted()
+        sys.exit(0)
+    if sys.argv[1:3] == ["--add", "research"]:
+        for name, make in tables:
+            add_module(name, make(), run_reference_research, "research")
         sys.exit(0)
     for name, make in tables:
         (add_gp1d if only_gp1d else save)(name, make())

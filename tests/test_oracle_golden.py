@@ -45,6 +45,12 @@ def test_per_band_gp_matches_reference(golden, fixture):
     _check(golden[fixture], "gp1d", rtol=1e-6, skip_obj=(TIE_OBJECT,) if fixture == "ref_edge" else ())
 
 
+@pytest.mark.parametrize("fixture", ["ref_sparse", "ref_dense", "ref_edge", "ref_c1_256"])
+def test_research_block_matches_reference(golden, fixture):
+    # SURVEY 8(f) row 3, oracle stage: research_features.py (v115c) restated with the reference's own numpy / scipy calls
+    _check(golden[fixture], "research", rtol=1e-12, skip_obj=(TIE_OBJECT,) if fixture == "ref_edge" else ())
+
+
 def test_absent_object_is_omitted(golden):
     g = golden["ref_edge"]
     assert 20 not in g["statistical_present"]            # object 20 has no rows (statistical.py:163-165)
