@@ -15,6 +15,7 @@ from hostsim.build import build
 from mallorn_astrophysics_b200 import schema
 
 P = ctypes.c_void_p
+ALL_COLUMNS = dict(schema.MODULE_COLUMNS, **schema.ORACLE_ONLY_COLUMNS)
 
 
 def make_fuzz(n_obj, seed):
@@ -58,8 +59,9 @@ def reference_frames(obj, band, t, f, e, z, n_obj):
     from features.lightcurve_shape import extract_shape_features_single
     from features.tde_physics import extract_tde_physics_features_single
     from features.physics_based import extract_physics_features_single
+    from features.research_features import extract_research_features_single
     names = np.array(list("ugrizy"))
-    out = {m: (np.arange(n_obj), np.full((n_obj, len(schema.MODULE_COLUMNS[m])), np.nan)) for m in ("statistical", "colors", "shape", "tde", "physics")}
+    out = {m: (np.arange(n_obj), np.full((n_obj, len(ALL_COLUMNS[m])), np.nan)) for m in ("statistical", "colors", "shape", "tde", "physics", "research")}
     raised = {}
     with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
         warnings.simplefilter("ignore")
@@ -68,14 +70,15 @@ def reference_frames(obj, band, t, f, e, z, n_obj):
             lc = pd.DataFrame({"object_id": f"o{k}", "Time (MJD)": t[mk], "Flux": f[mk], "Flux_err": e[mk], "Filter": names[band[mk]]})
             calls = {"statistical": lambda: extract_statistical_features(lc, [f"o{k}"]).iloc[0].to_dict(),
                      "colors": lambda: extract_color_features_single(lc), "shape": lambda: extract_shape_features_single(lc),
-                     "tde": lambda: extract_tde_physics_features_single(lc), "physics": lambda: extract_physics_features_single(lc, z[k])}
+                     "tde": lambda: extract_tde_physics_features_single(lc), "physics": lambda: extract_physics_features_single(lc, z[k]),
+                     "research": lambda: extract_research_features_single(lc, {"Z": z[k]})}
             for m, call in calls.items():
                 try:
                     d = call()
                 except Exception as exc:                      # noqa: BLE001 -- the point is to see what upstream does
                     raised.setdefault(m, []).append((k, type(exc).__name__))
                     continue
-                for c_i, c in enumerate(schema.MODULE_COLUMNS[m]):
+                for c_i, c in enumerate(ALL_COLUMNS[m]):
                     if c in d:
                         out[m][1][k, c_i] = float(d[c])
     out["_raised"] = raised
@@ -90,7 +93,8 @@ def main(n_obj=None, seed=None):
     lib = ctypes.CDLL(build())
     pk = pack_reference(obj, band, t, f, e, n_obj)
     ref = reference_frames(obj, band, t, f, e, z, n_obj)
-    fns = {"statistical": ("hs_stat", False), "colors": ("hs_color", True), "shape": ("hs_shape", True), "tde": ("hs_tde", True), "physics": ("hs_physics", True)}
+    fns = {"statistical": ("hs_stat", False), "colors": ("hs_color", True), "shape": ("hs_shape", True), "tde": ("hs_tde", True), "physics": ("hs_physics", True),
+           "research": ("hs_research", True)}
     total_bad = 0
     total_defined = [0]
     # objects whose answer is not defined upstream: equal times inside a band (or anywhere, for the all-band columns)
@@ -103,7 +107,7 @@ def main(n_obj=None, seed=None):
         tie_band[k] = any(len(np.unique(tk[bk == b])) < (bk == b).sum() for b in range(6))
     print(f"{n_obj} objects: {int(tie_band.sum())} with equal times inside a band, {int(tie_any.sum())} with equal times anywhere")
     for m, (fn, takes_z) in fns.items():
-        ncol = len(schema.MODULE_COLUMNS[m])
+        ncol = len(ALL_COLUMNS[m])
         out = np.zeros((n_obj, ncol))
         args = [ctypes.c_longlong(n_obj)] + [pk[k].ctypes.data_as(P) for k in ("seg_off", "t", "flux", "err", "rank")]
         if takes_z:
@@ -123,7 +127,7 @@ def main(n_obj=None, seed=None):
         bad = nan_bad | val_bad
         total_bad += int(bad.sum())
         print(f"{m}: {len(present)} objects, NaN-pattern mismatches {int(nan_bad.sum())}, value mismatches {int(val_bad.sum())}")
-        cols = schema.MODULE_COLUMNS[m]
+        cols = ALL_COLUMNS[m]
         seen = {}
         for i, j in np.argwhere(bad):
             seen.setdefault(cols[j], []).append((int(present[i]), got[i, j], want[i, j]))

@@ -11,6 +11,7 @@
 #include "shape.cuh"
 #include "tde.cuh"
 #include "physics.cuh"
+#include "research.cuh"
 #include "gp_host.hpp"
 #include "fits_thread.cuh"
 #include "gp1d.cuh"
@@ -84,6 +85,21 @@ HS_PASS(hs_color, COLOR_COLS, color_row(tm, v, s.sa.data(), s.sb.data(), s.row.d
 HS_PASS(hs_shape, SHAPE_COLS, shape_row(tm, v, s.sa.data(), s.sb.data(), s.row.data()))
 HS_PASS(hs_tde, TDE_COLS, tde_row(tm, v, s.sa.data(), s.sb.data(), s.sc.data(), s.sd.data(), s.row.data()))
 HS_PASS(hs_physics, PHYSICS_COLS, physics_row(tm, v, zz, s.sa.data(), s.sb.data(), s.row.data()))
+
+// research block (research.cuh): extra scratch for the 1-day grid of the r band and the wavelet
+int hs_research(long long n_obj, const long long* seg_off, const double* t, const double* f, const double* e,
+                const unsigned short* rank, const double* z, double* out) {
+  HostTeam tm;
+  Scratch s(2 * MAX_OBS);
+  std::vector<double> grid(16384), wav(MHPS_WAVELET_CAP);
+  for (long long o = 0; o < n_obj; ++o) {
+    ObjView v;
+    stage_object(tm, seg_off, t, f, e, rank, o, s.t.data(), s.f.data(), s.e.data(), s.rank.data(), v);
+    research_row(tm, v, z ? z[o] : qnan(), s.sa.data(), s.sb.data(), s.sc.data(), grid.data(), (int)grid.size(), wav.data(), s.row.data());
+    std::memcpy(out + o * RESEARCH_COLS, s.row.data(), sizeof(double) * RESEARCH_COLS);
+  }
+  return 0;
+}
 
 // one-thread-per-fit variants (trf_thread.cuh / fits_thread.cuh)
 int hs_bazin_t(long long n_obj, const long long* seg_off, const double* t, const double* f, const double* e,

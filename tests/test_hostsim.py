@@ -191,3 +191,18 @@ def test_register_tiled_objective_lane_emulation(golden, hs, force_tpl):
     ok = ~np.isnan(base)
     assert np.array_equal(np.isnan(out), np.isnan(base))
     np.testing.assert_allclose(out[ok], base[ok], rtol=1e-4, atol=1e-8)
+
+
+@pytest.mark.parametrize("fixture", ["ref_sparse", "ref_dense", "ref_edge", "ref_c1_256"])
+def test_research_template_matches_reference(golden, hs, fixture):
+    """research.cuh (power-law quality, nuclear proxies, colour at peak, Mexican-hat power spectra,
+    luminosity) host instantiation vs the reference's own frames"""
+    g = golden[fixture]
+    pk, n_obj = _pack(g)
+    out, _ = _run(hs, "hs_research", 40, pk, n_obj, z=g["z"])
+    pres, ref = g["research_present"], g["research_rows"]
+    keep = pres != (TIE_OBJECT if fixture == "ref_edge" else -1)
+    got, ref = out[pres][keep], ref[keep]
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    np.testing.assert_allclose(got[ok], ref[ok], rtol=1e-7, atol=1e-9)
