@@ -42,6 +42,7 @@ extern "C" {
 #define MLRN_POWERLAW_COLS 27   /* extract_powerlaw_features      scripts/train_v55_powerlaw.py:196 */
 #define MLRN_GP2D_COLS 27       /* extract_multiband_gp_features  multiband_gp.py:347     */
 #define MLRN_GP1D_COLS 21       /* extract_gp_features            gaussian_process.py:251 */
+#define MLRN_RESEARCH_COLS 40   /* extract_research_features      research_features.py:566 (experimental) */
 #define MLRN_SEGMETA_COLS 22    /* K1 integer outputs per object, see mlrn_store_segments */
 
 typedef struct mlrn_store mlrn_store;   /* packed, device-resident light curves of one batch */
@@ -93,6 +94,13 @@ int mlrn_gp2d(const mlrn_store* s, double* out, int32_t* status, int out_on_devi
  * status (optional): int32 [n_obj, 4, 3] = per band {objective evaluations over the four starts, L-BFGS-B
  * iterations over the four starts, index of the winning start (-1: band not fitted)} */
 int mlrn_gp1d(const mlrn_store* s, double* out, int32_t* status, int out_on_device, void* stream);
+
+/* EXPERIMENTAL -- "research" block of the v115c model (power-law decay quality, nuclear-position proxies, colour at
+ * peak, Mexican-hat power spectra of the r band on a 1-day grid, luminosity; research_features.py:44-560).  The
+ * arithmetic is verified against the reference on the CPU; the CUDA pass has not been validated on a GPU yet and is not
+ * part of the default pipeline.  z: redshift per object or NULL (luminosity columns NaN, as for Z <= 0 upstream :556);
+ * r-band coverage beyond 8192 days leaves the six mhps_* columns NaN. */
+int mlrn_research(const mlrn_store* s, const double* z, int z_on_device, double* out, int out_on_device, void* stream);
 
 #ifdef __cplusplus
 }

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MLRN_LIB") or os.path.join(HERE, "libmallorn_b200.so")   # MLRN_LIB: developer builds (profiling flags)
 
 COLS = {"statistical": 123, "colors": 83, "shape": 65, "tde": 25, "physics": 32,
-        "bazin": 52, "powerlaw": 27, "gp2d": 27, "gp1d": 21}
+        "bazin": 52, "powerlaw": 27, "gp2d": 27, "gp1d": 21, "research": 40}
 SEGMETA_COLS = 22
 N_SEG = 7
 MAX_OBS = 1024
@@ -50,8 +50,9 @@ def lib() -> C.CDLL:
     for name in ("mlrn_stat", "mlrn_color", "mlrn_shape", "mlrn_tde"):
         if hasattr(L, name):
             getattr(L, name).argtypes = [vp, vp, C.c_int, vp]
-    if hasattr(L, "mlrn_physics"):
-        L.mlrn_physics.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp]
+    for name in ("mlrn_physics", "mlrn_research"):
+        if hasattr(L, name):
+            getattr(L, name).argtypes = [vp, vp, C.c_int, vp, C.c_int, vp]
     for name in ("mlrn_bazin", "mlrn_powerlaw", "mlrn_gp2d", "mlrn_gp1d"):
         if hasattr(L, name):
             getattr(L, name).argtypes = [vp, vp, vp, C.c_int, vp]

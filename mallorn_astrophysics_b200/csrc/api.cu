@@ -28,6 +28,7 @@ int run_bazin(const mlrn_store* s, double* out_dev, int* status_dev, cudaStream_
 int run_powerlaw(const mlrn_store* s, double* out_dev, int* status_dev, cudaStream_t st);
 int run_gp2d(const mlrn_store* s, double* out_dev, int* status_dev, cudaStream_t st);
 int run_gp1d(const mlrn_store* s, double* out_dev, int* status_dev, cudaStream_t st);
+int run_research(const mlrn_store* s, const double* z_dev, double* out_dev, cudaStream_t st);
 }  // namespace mlrn
 
 using mlrn::set_error;
@@ -217,6 +218,22 @@ int mlrn_physics(const mlrn_store* s, const double* z, int z_on_device, double* 
     zd = ztmp;
   }
   int rc = with_output(s, out, out_on_device, MLRN_PHYSICS_COLS, st, [&](double* d) { return mlrn::run_physics(s, zd, d, st); });
+  if (ztmp) cudaFreeAsync(ztmp, st);
+  return rc;
+}
+
+int mlrn_research(const mlrn_store* s, const double* z, int z_on_device, double* out, int out_on_device, void* stream) {
+  if (!s) { set_error("null store"); return MLRN_EINVAL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  DevGuard g(s->device);
+  const double* zd = z;                                   // NULL = no redshifts: the luminosity columns are NaN
+  double* ztmp = nullptr;
+  if (z && !z_on_device && s->n_obj > 0) {
+    MLRN_CUDA(cudaMallocAsync(&ztmp, sizeof(double) * (size_t)s->n_obj, st));
+    MLRN_CUDA(cudaMemcpyAsync(ztmp, z, sizeof(double) * (size_t)s->n_obj, cudaMemcpyHostToDevice, st));
+    zd = ztmp;
+  }
+  int rc = with_output(s, out, out_on_device, MLRN_RESEARCH_COLS, st, [&](double* d) { return mlrn::run_research(s, zd, d, st); });
   if (ztmp) cudaFreeAsync(ztmp, st);
   return rc;
 }

@@ -32,13 +32,13 @@ def run_frame_modules(modules: Sequence[str], lightcurves, object_ids: Optional[
     store, ids = LightCurveStore.from_frame(lightcurves, object_ids, device=device)
     try:
         z = None
-        if "physics" in modules:
+        if "physics" in modules or ("research" in modules and metadata is not None):
             # z_lookup = dict(zip(metadata['object_id'], metadata['Z'])): the LAST duplicate wins
             # (physics_based.py:481); ids missing from the metadata get NaN (:496)
             zmap = pd.Series(metadata["Z"].to_numpy(dtype=np.float64), index=metadata["object_id"].to_numpy())
             zmap = zmap[~zmap.index.duplicated(keep="last")]
             z = zmap.reindex(ids).to_numpy(dtype=np.float64)
-        rows = {m: store.features(m, z=z if m == "physics" else None) for m in modules}
+        rows = {m: store.features(m, z=z if m in ("physics", "research") else None) for m in modules}
         counts = store.segments()[:, 0:21:3].sum(axis=1)
     finally:
         store.close()

@@ -121,9 +121,9 @@ MODULE_COLUMNS = {
     "statistical": STAT_COLUMNS, "colors": COLOR_COLUMNS, "shape": SHAPE_COLUMNS,
     "tde": TDE_COLUMNS, "physics": PHYSICS_COLUMNS, "bazin": BAZIN_COLUMNS,
     "powerlaw": POWERLAW_COLUMNS, "gp2d": GP2D_COLUMNS, "gp1d": GP1D_COLUMNS,
+    "research": RESEARCH_COLUMNS,       # experimental pass (mlrn_research): not in the default pipeline yet
 }
-# SURVEY 8(f) row 3, oracle stage only (no CUDA pass yet): not part of MODULE_COLUMNS / the C-ABI
-ORACLE_ONLY_COLUMNS = {"research": RESEARCH_COLUMNS}
+ORACLE_ONLY_COLUMNS = {}
 assert len(RESEARCH_COLUMNS) == 40
 
 assert len(STAT_COLUMNS) == 123 and len(COLOR_COLUMNS) == 83 and len(SHAPE_COLUMNS) == 65

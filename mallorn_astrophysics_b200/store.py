@@ -143,11 +143,12 @@ class LightCurveStore:
         optr, okeep, odev = _ptr(out, np.float64)
         if not _is_torch(out) and okeep is not out:
             raise ValueError("out must be a C-contiguous float64 array")
-        if module == "physics":
+        if module in ("physics", "research"):
             if z is None:
                 z = np.full(self.n_obj, np.nan)
             zptr, zkeep, zdev = _ptr(z, np.float64)
-            rc = L.mlrn_physics(self._h, zptr, 1 if zdev else 0, optr, 1 if odev else 0, st)
+            fn = L.mlrn_physics if module == "physics" else L.mlrn_research
+            rc = fn(self._h, zptr, 1 if zdev else 0, optr, 1 if odev else 0, st)
         elif module in ("bazin", "powerlaw", "gp2d", "gp1d"):
             sptr = 0
             if status is not None:

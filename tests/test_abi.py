@@ -50,7 +50,7 @@ def test_schema_matches_header(native):
     from mallorn_astrophysics_b200 import schema
     hdr = open(os.path.join(ROOT, "include", "mallorn_b200.h")).read()
     for mod, macro in (("statistical", "STAT"), ("colors", "COLOR"), ("shape", "SHAPE"), ("tde", "TDE"),
-                       ("physics", "PHYSICS"), ("bazin", "BAZIN"), ("powerlaw", "POWERLAW"), ("gp2d", "GP2D"), ("gp1d", "GP1D")):
+                       ("physics", "PHYSICS"), ("bazin", "BAZIN"), ("powerlaw", "POWERLAW"), ("gp2d", "GP2D"), ("gp1d", "GP1D"), ("research", "RESEARCH")):
         n = int(re.search(rf"#define MLRN_{macro}_COLS (\d+)", hdr).group(1))
         assert n == len(schema.MODULE_COLUMNS[mod]) == native.COLS[mod]
 
@@ -65,7 +65,7 @@ def test_features_package_imports_under_both_names():
             "from features.colors import extract_color_features; from features.lightcurve_shape import extract_shape_features; "
             "from features.physics_based import extract_physics_features; from features.tde_physics import extract_tde_physics_features; "
             "from features.bazin_fitting import extract_bazin_features, bazin_function; "
-            "from features.multiband_gp import extract_multiband_gp_features; from features.gaussian_process import extract_gp_features; from features.powerlaw import extract_powerlaw_features; "
+            "from features.multiband_gp import extract_multiband_gp_features; from features.gaussian_process import extract_gp_features; from features.research_features import extract_research_features; from features.powerlaw import extract_powerlaw_features; "
             "import features; assert features.extract_statistical_features is extract_statistical_features; "
             "assert LSST_BANDS == list('ugrizy'); print('ok')") % os.path.join(ROOT, "mallorn_astrophysics_b200")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
