@@ -25,7 +25,6 @@
 #include <string>
 #include <string_view>
 #include <thread>
-#include <unordered_map>
 #include <vector>
 #include <fcntl.h>
 #include <sys/mman.h>
@@ -58,14 +57,11 @@ const double P10[] = {
 inline bool is_digit(char c) { return c >= '0' && c <= '9'; }
 inline bool is_space(char c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
 
-// pandas' default converter (17 significant digits, one scaling by a power of ten).  Returns false if the
-// field is not a number in that grammar (the caller then tries the NaN / infinity spellings).
-bool pandas_strtod(const char* p, const char* end, double& out) {
-  while (p < end && is_space(*p)) ++p;
-  while (end > p && is_space(end[-1])) --end;
-  if (p == end) return false;
+// pandas' default converter (17 significant digits, one scaling by a power of ten), from the first character of the
+// number.  Consumes the longest prefix that is a number in that grammar; returns false if there is none.
+inline bool pandas_number_prefix(const char* p, const char* end, double& out, const char*& stop) {
   bool neg = false;
-  if (*p == '-') { neg = true; ++p; } else if (*p == '+') ++p;
+  if (p < end && *p == '-') { neg = true; ++p; } else if (p < end && *p == '+') ++p;
   // The reference accumulates number = number * 10 + digit in a double.  Up to 15 digits every partial value is an
   // exactly representable integer, so those are gathered in a uint64 (no floating-point dependency chain) and only
   // digits 16 and 17 -- where the double accumulation rounds -- are added the reference's way.
@@ -102,15 +98,24 @@ bool pandas_strtod(const char* p, const char* end, double& out) {
     if (nd == 0) p = save;
     else exponent += eneg ? -n : n;
   }
-  if (p != end) return false;
   if (exponent > 308) number = neg ? -HUGE_VAL : HUGE_VAL;
   else if (exponent > 0) number *= P10[exponent];
   else if (exponent < -308) {
     if (exponent < -616) number = neg ? -0.0 : 0.0;
     else { number /= P10[-308 - exponent]; number /= P10[308]; }
-  } else number /= P10[-exponent];
+  } else if (exponent < 0) number /= P10[-exponent];
   out = number;
+  stop = p;
   return true;
+}
+
+// a whole field: optional surrounding white space, then nothing but the number
+bool pandas_strtod(const char* p, const char* end, double& out) {
+  while (p < end && is_space(*p)) ++p;
+  while (end > p && is_space(end[-1])) --end;
+  if (p == end) return false;
+  const char* stop;
+  return pandas_number_prefix(p, end, out, stop) && stop == end;
 }
 
 bool ieq(std::string_view a, const char* b) {
@@ -157,6 +162,45 @@ std::string_view strip(std::string_view s) {
   return s;
 }
 
+// id string -> dense code: open addressing, power-of-two capacity, the 64-bit hash kept beside the key so that a probe
+// compares one word before touching the string (std::unordered_map spent half of the parse time here)
+inline uint64_t hash_bytes(const char* p, size_t n) {
+  uint64_t h = 0x9E3779B97F4A7C15ull ^ (n * 0xff51afd7ed558ccdull);
+  while (n >= 8) { uint64_t w; memcpy(&w, p, 8); h = (h ^ w) * 0x9FB21C651E98DF25ull; h ^= h >> 29; p += 8; n -= 8; }
+  uint64_t w = 0; memcpy(&w, p, n);
+  h = (h ^ w) * 0x9FB21C651E98DF25ull;
+  return h ^ (h >> 32);
+}
+struct IdTable {
+  struct Slot { uint64_t h; uint32_t off; uint32_t n; int32_t code; };      // code < 0: empty
+  std::vector<Slot> slots; size_t used = 0;
+  std::vector<char> arena;             // key bytes copied here: comparing against the first occurrence inside the mapped
+                                       // file was a cache and TLB miss per row
+  IdTable() : slots(2048, Slot{0, 0, 0, -1}) { arena.reserve(1 << 16); }
+  void grow() {
+    std::vector<Slot> old; old.swap(slots);
+    slots.assign(old.size() * 2, Slot{0, 0, 0, -1});
+    for (const Slot& s : old) if (s.code >= 0) { size_t i = s.h & (slots.size() - 1); while (slots[i].code >= 0) i = (i + 1) & (slots.size() - 1); slots[i] = s; }
+  }
+  // returns the code of `id`, inserting it with `next_code` if new (then inserted = true)
+  int32_t find_or_insert(std::string_view id, int32_t next_code, bool& inserted) {
+    const uint64_t h = hash_bytes(id.data(), id.size());
+    size_t i = h & (slots.size() - 1);
+    for (;;) {
+      Slot& s = slots[i];
+      if (s.code < 0) {
+        s = Slot{h, (uint32_t)arena.size(), (uint32_t)id.size(), next_code};
+        arena.insert(arena.end(), id.begin(), id.end());
+        inserted = true;
+        if (++used * 2 > slots.size()) grow();
+        return next_code;
+      }
+      if (s.h == h && s.n == id.size() && memcmp(arena.data() + s.off, id.data(), id.size()) == 0) { inserted = false; return s.code; }
+      i = (i + 1) & (slots.size() - 1);
+    }
+  }
+};
+
 struct Chunk {
   const char* begin; const char* end; const Columns* cols;
   int64_t rows = 0, row0 = 0;
@@ -194,8 +238,7 @@ int64_t count_rows(const char* b, const char* e) {
 }
 
 void parse_chunk(Chunk& c, mlrn_table& tb, std::vector<int32_t>& local_code) {
-  std::unordered_map<std::string_view, int32_t> seen;
-  seen.reserve(1024);
+  IdTable seen;
   const Columns& col = *c.cols;
   int64_t r = c.row0;
   const char* p = c.begin;
@@ -206,32 +249,35 @@ void parse_chunk(Chunk& c, mlrn_table& tb, std::vector<int32_t>& local_code) {
     const char* next = nl ? nl + 1 : c.end;
     while (le > p && le[-1] == '\r') --le;
     if (le == p) { p = next; continue; }
-    // split the line on commas (the light-curve files have no quoted commas)
+    // one pass over the line (the light-curve files have no quoted commas): numeric fields are converted where they
+    // stand -- the number parser stops at the comma -- and only the id / Filter fields are scanned for their end
     int k = 0;
-    const char* fb = p;
-    std::string_view idv, bandv; const char *tb_ = nullptr, *te = nullptr, *fb_ = nullptr, *fe = nullptr, *eb = nullptr, *ee = nullptr;
-    for (const char* q = p;; ++q) {
-      if (q == le || *q == ',') {
-        if (k == col.id) idv = strip(std::string_view(fb, (size_t)(q - fb)));
+    std::string_view idv, bandv;
+    double num[3] = {std::numeric_limits<double>::quiet_NaN(), std::numeric_limits<double>::quiet_NaN(), std::numeric_limits<double>::quiet_NaN()};
+    const char* q = p;
+    for (;; ++k) {
+      const char* fb = q;
+      const int which = (k == col.t) ? 0 : (k == col.f) ? 1 : (k == col.e) ? 2 : -1;
+      const char* stop;
+      if (which >= 0 && pandas_number_prefix(fb, le, num[which], stop) && (stop == le || *stop == ',')) q = stop;
+      else {
+        while (q < le && *q != ',') ++q;
+        if (which >= 0) num[which] = parse_number(fb, q, c.bad_number);         // blanks, NaN spellings, infinities
+        else if (k == col.id) idv = strip(std::string_view(fb, (size_t)(q - fb)));
         else if (k == col.band) bandv = strip(std::string_view(fb, (size_t)(q - fb)));
-        else if (k == col.t) { tb_ = fb; te = q; }
-        else if (k == col.f) { fb_ = fb; fe = q; }
-        else if (k == col.e) { eb = fb; ee = q; }
-        ++k; fb = q + 1;
-        if (q == le) break;
       }
+      if (q == le) { ++k; break; }
+      ++q;
     }
     if (k != col.count) c.bad_line = true;
-    tb.t[r] = tb_ ? parse_number(tb_, te, c.bad_number) : std::numeric_limits<double>::quiet_NaN();
-    tb.flux[r] = fb_ ? parse_number(fb_, fe, c.bad_number) : std::numeric_limits<double>::quiet_NaN();
-    tb.err[r] = eb ? parse_number(eb, ee, c.bad_number) : std::numeric_limits<double>::quiet_NaN();
+    tb.t[r] = num[0]; tb.flux[r] = num[1]; tb.err[r] = num[2];
     tb.band[r] = band_code(bandv);
     int32_t code = -1;
     if (idv == prev_id && prev_code >= 0) code = prev_code;   // real files list an object's rows together
     else if (!is_na_token(idv)) {
-      auto it = seen.find(idv);
-      if (it == seen.end()) { code = (int32_t)c.local_ids.size(); seen.emplace(idv, code); c.local_ids.push_back(idv); }
-      else code = it->second;
+      bool fresh = false;
+      code = seen.find_or_insert(idv, (int32_t)c.local_ids.size(), fresh);
+      if (fresh) c.local_ids.push_back(idv);
     }
     local_code[r] = code;
     prev_id = idv; prev_code = code;
@@ -324,19 +370,18 @@ int mlrn_ingest_csv(const char* const* paths, int n_paths, int n_threads, mlrn_t
     if (c.bad_number) { delete tb; g_err = "a Time/Flux/Flux_err field is not a number"; return MLRN_INGEST_EFORMAT; }
   }
   // global ids in order of first appearance over the concatenated files (== pd.concat(...)['object_id'].unique())
-  std::unordered_map<std::string_view, int32_t> global;
+  IdTable global;
   tb->id_off.push_back(0);
   for (auto& c : chunks) {
     c.local_to_global.resize(c.local_ids.size());
     for (size_t k = 0; k < c.local_ids.size(); ++k) {
-      auto it = global.find(c.local_ids[k]);
-      if (it == global.end()) {
-        int32_t gid = (int32_t)global.size();
-        global.emplace(c.local_ids[k], gid);
+      bool fresh = false;
+      const int32_t gid = global.find_or_insert(c.local_ids[k], (int32_t)(tb->id_off.size() - 1), fresh);
+      if (fresh) {
         tb->id_chars.append(c.local_ids[k].data(), c.local_ids[k].size());
         tb->id_off.push_back((int64_t)tb->id_chars.size());
-        c.local_to_global[k] = gid;
-      } else c.local_to_global[k] = it->second;
+      }
+      c.local_to_global[k] = gid;
     }
   }
   run_parallel(nc, n_threads, [&](int j) {
