@@ -121,3 +121,43 @@ def test_ingest_header_symbols_are_exported(ingest):
     assert len(names) >= 12
     L = ingest.lib()
     assert not [n for n in names if not hasattr(L, n)]
+
+
+def test_number_grammar_adversarial_spellings(ingest, tmp_path):
+    """digit strings built to hit every branch of the converter: more than 17 digits before / after the point, leading
+    zeros, huge and tiny exponents, signs, bare points, exponent markers without digits"""
+    rng = np.random.default_rng(23)
+    digits = lambda n: "".join(rng.choice(list("0123456789"), n)) if n else ""
+    texts = []
+    for _ in range(3000):
+        a, b = int(rng.integers(0, 25)), int(rng.integers(0, 25))
+        if a == 0 and b == 0:
+            a = 1
+        s = rng.choice(["", "-", "+"]) + ("0" * int(rng.integers(0, 4)) if rng.random() < 0.3 else "") + digits(a)
+        if b or rng.random() < 0.2:
+            s += "." + digits(b)
+        r = rng.random()
+        if r < 0.35:
+            s += rng.choice(["e", "E"]) + rng.choice(["", "-", "+"]) + str(int(rng.integers(0, 420)))
+        elif r < 0.38:
+            s += "e"                      # not a number for pandas either: the column would become strings
+        texts.append(s)
+    numeric = []
+    for s in texts:
+        col = pd.read_csv(io.StringIO(f"a,b\n{s},1\n"), dtype={"a": str})["a"].iloc[0]      # what pandas sees as text
+        try:
+            val = pd.read_csv(io.StringIO(f"a,b\n{s},1\n1.5,1\n"))["a"]
+            if val.dtype == np.float64:
+                numeric.append((s, float(val.iloc[0])))
+        except Exception:
+            pass
+    assert len(numeric) > 2500
+    p = tmp_path / "adv.csv"
+    with open(p, "w") as fh:
+        fh.write("object_id,Time (MJD),Flux,Flux_err,Filter\n")
+        for s, _ in numeric:
+            fh.write(f"a,1.5,{s},1.0,g\n")
+    got = ingest.read_lightcurve_csv(p).flux
+    want = np.array([v for _, v in numeric])
+    same = (got.view(np.uint64) == want.view(np.uint64)) | (np.isnan(got) & np.isnan(want))
+    assert same.all(), [(numeric[i][0], got[i], want[i]) for i in np.flatnonzero(~same)[:5]]
