@@ -211,9 +211,21 @@ struct Chunk {
 
 }  // namespace
 
+namespace {
+// column storage without the zero fill of std::vector: the pages are first touched by the thread that parses into them
+template <class T>
+struct Buf {
+  T* p = nullptr;
+  bool alloc(size_t n) { p = static_cast<T*>(malloc(n ? n * sizeof(T) : 1)); return p != nullptr; }
+  ~Buf() { free(p); }
+  T* data() const { return p; }
+  T& operator[](size_t i) const { return p[i]; }
+};
+}  // namespace
+
 struct mlrn_table {
   int64_t n_rows = 0;
-  std::vector<int32_t> obj; std::vector<uint8_t> band; std::vector<double> t, flux, err;
+  Buf<int32_t> obj; Buf<uint8_t> band; Buf<double> t, flux, err;
   std::vector<int64_t> id_off; std::string id_chars;
 };
 
@@ -237,7 +249,7 @@ int64_t count_rows(const char* b, const char* e) {
   return n;
 }
 
-void parse_chunk(Chunk& c, mlrn_table& tb, std::vector<int32_t>& local_code) {
+void parse_chunk(Chunk& c, mlrn_table& tb) {          // tb.obj receives chunk-local codes, made global afterwards
   IdTable seen;
   const Columns& col = *c.cols;
   int64_t r = c.row0;
@@ -279,7 +291,7 @@ void parse_chunk(Chunk& c, mlrn_table& tb, std::vector<int32_t>& local_code) {
       code = seen.find_or_insert(idv, (int32_t)c.local_ids.size(), fresh);
       if (fresh) c.local_ids.push_back(idv);
     }
-    local_code[r] = code;
+    tb.obj[r] = code;
     prev_id = idv; prev_code = code;
     ++r;
     p = next;
@@ -357,14 +369,10 @@ int mlrn_ingest_csv(const char* const* paths, int n_paths, int n_threads, mlrn_t
   if (total > 2147483647LL) { g_err = "more than 2^31-1 rows: ingest in several batches"; return MLRN_INGEST_EINVAL; }
   mlrn_table* tb = new (std::nothrow) mlrn_table();
   if (!tb) { g_err = "out of memory"; return MLRN_INGEST_EIO; }
-  std::vector<int32_t> local_code;
-  try {
-    tb->n_rows = total;
-    tb->obj.resize((size_t)total); tb->band.resize((size_t)total);
-    tb->t.resize((size_t)total); tb->flux.resize((size_t)total); tb->err.resize((size_t)total);
-    local_code.resize((size_t)total);
-  } catch (const std::bad_alloc&) { delete tb; g_err = "out of memory"; return MLRN_INGEST_EIO; }
-  run_parallel(nc, n_threads, [&](int j) { parse_chunk(chunks[(size_t)j], *tb, local_code); });
+  tb->n_rows = total;
+  if (!(tb->obj.alloc((size_t)total) && tb->band.alloc((size_t)total) && tb->t.alloc((size_t)total) &&
+        tb->flux.alloc((size_t)total) && tb->err.alloc((size_t)total))) { delete tb; g_err = "out of memory"; return MLRN_INGEST_EIO; }
+  run_parallel(nc, n_threads, [&](int j) { parse_chunk(chunks[(size_t)j], *tb); });
   for (auto& c : chunks) {
     if (c.bad_line) { delete tb; g_err = "a data line does not have the header's number of fields"; return MLRN_INGEST_EFORMAT; }
     if (c.bad_number) { delete tb; g_err = "a Time/Flux/Flux_err field is not a number"; return MLRN_INGEST_EFORMAT; }
@@ -387,7 +395,7 @@ int mlrn_ingest_csv(const char* const* paths, int n_paths, int n_threads, mlrn_t
   run_parallel(nc, n_threads, [&](int j) {
     const Chunk& c = chunks[(size_t)j];
     for (int64_t r = c.row0; r < c.row0 + c.rows; ++r) {
-      const int32_t lc = local_code[(size_t)r];
+      const int32_t lc = tb->obj[(size_t)r];
       tb->obj[(size_t)r] = lc < 0 ? -1 : c.local_to_global[(size_t)lc];
     }
   });

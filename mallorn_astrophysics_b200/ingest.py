@@ -76,15 +76,31 @@ class LightCurveColumns:
                              "Flux_err": self.err, "Filter": bands[self.band]})
 
 
-def _copy(ptr, n, dtype):
+class _Table:
+    """Owns one ``mlrn_table``; freed when the last array that views its columns is garbage-collected."""
+
+    def __init__(self, handle):
+        self.handle = handle
+
+    def __del__(self):
+        if self.handle:
+            lib().mlrn_table_free(self.handle)
+            self.handle = None
+
+
+def _view(owner: _Table, ptr, n: int, dtype) -> np.ndarray:
+    """Zero-copy numpy view of a column of the table; keeps ``owner`` (and so the C memory) alive."""
     if n == 0:
         return np.zeros(0, dtype=dtype)
-    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dtype))), shape=(n,)).copy()
+    buf = (np.ctypeslib.as_ctypes_type(dtype) * n).from_address(ptr)
+    buf._owner = owner                               # ctypes instances accept attributes; numpy keeps `buf` as .base
+    return np.frombuffer(buf, dtype=dtype)
 
 
 def read_lightcurve_csv(paths: Union[str, Path, Sequence[Union[str, Path]]], threads: int = 0) -> LightCurveColumns:
     """Parse one or more light-curve CSV files as one concatenated table.  Structural problems (missing column,
-    ragged line, non-numeric field, unreadable file) raise ``MallornIngestError``."""
+    ragged line, non-numeric field, unreadable file) raise ``MallornIngestError``.  The returned arrays are views of the
+    parser's own buffers (no copy); they stay valid for as long as any of them is referenced."""
     if isinstance(paths, (str, Path)):
         paths = [paths]
     L = lib()
@@ -94,18 +110,16 @@ def read_lightcurve_csv(paths: Union[str, Path, Sequence[Union[str, Path]]], thr
     rc = L.mlrn_ingest_csv(arr, len(enc), int(threads), C.byref(h))
     if rc != 0:
         raise MallornIngestError(f"mlrn_ingest_csv failed (code {rc}): {L.mlrn_ingest_last_error().decode()}")
-    try:
-        n, k = L.mlrn_table_rows(h), L.mlrn_table_objects(h)
-        off = _copy(L.mlrn_table_id_offsets(h), k + 1, np.int64)
-        chars = C.string_at(L.mlrn_table_id_chars(h), L.mlrn_table_id_bytes(h)) if k else b""
-        ids = np.empty(k, dtype=object)
-        for i in range(k):
-            ids[i] = chars[off[i]:off[i + 1]].decode()
-        return LightCurveColumns(_copy(L.mlrn_table_obj(h), n, np.int32), _copy(L.mlrn_table_band(h), n, np.uint8),
-                                 _copy(L.mlrn_table_time(h), n, np.float64), _copy(L.mlrn_table_flux(h), n, np.float64),
-                                 _copy(L.mlrn_table_err(h), n, np.float64), ids)
-    finally:
-        L.mlrn_table_free(h)
+    owner = _Table(h)
+    n, k = L.mlrn_table_rows(h), L.mlrn_table_objects(h)
+    off = _view(owner, L.mlrn_table_id_offsets(h), k + 1, np.int64)
+    chars = C.string_at(L.mlrn_table_id_chars(h), L.mlrn_table_id_bytes(h)) if k else b""
+    ids = np.empty(k, dtype=object)
+    for i in range(k):
+        ids[i] = chars[off[i]:off[i + 1]].decode()
+    return LightCurveColumns(_view(owner, L.mlrn_table_obj(h), n, np.int32), _view(owner, L.mlrn_table_band(h), n, np.uint8),
+                             _view(owner, L.mlrn_table_time(h), n, np.float64), _view(owner, L.mlrn_table_flux(h), n, np.float64),
+                             _view(owner, L.mlrn_table_err(h), n, np.float64), ids)
 
 
 def load_lightcurves(split: str = "train", data_path: Union[str, Path, None] = None, threads: int = 0) -> LightCurveColumns:
