@@ -15,6 +15,10 @@ def test_reference_bazin_fit_moves_under_a_one_ulp_perturbation(golden):
     import bazin_ulp_sensitivity as sens
     from oracle import bazin as ob
     from fitparity import classify_bazin
+    x = np.random.default_rng(0).uniform(-30, 30, 50000)
+    if (np.exp(x) == sens.exp_libm(x)).all():
+        import pytest
+        pytest.skip("numpy's exp and libm's exp agree bit for bit on this machine: no perturbation to apply")
     g = golden["ref_edge"]
     a, b = sens.rows(g, ob.bazin), sens.rows(g, sens.bazin_libm)
     c = classify_bazin(b, a)
