@@ -55,6 +55,19 @@ const double P10[] = {
     1e300, 1e301, 1e302, 1e303, 1e304, 1e305, 1e306, 1e307, 1e308};
 
 inline bool is_digit(char c) { return c >= '0' && c <= '9'; }
+
+// eight ASCII digits at p -> their value (little-endian SWAR); false if any of the eight bytes is not a digit
+inline bool eight_digits(const char* p, uint64_t& val) {
+  uint64_t w;
+  memcpy(&w, p, 8);
+  const uint64_t hi = w + 0x4646464646464646ull, lo = w - 0x3030303030303030ull;
+  if (((hi | lo) & 0x8080808080808080ull) != 0) return false;
+  w = lo;
+  w = (w * 10) + (w >> 8);                                                      // pairs in bytes 0, 2, 4, 6
+  w = (((w & 0x000000FF000000FFull) * 0x000F424000000064ull) + (((w >> 16) & 0x000000FF000000FFull) * 0x0000271000000001ull)) >> 32;
+  val = w;
+  return true;
+}
 inline bool is_space(char c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
 
 // pandas' default converter (17 significant digits, one scaling by a power of ten), from the first character of the
@@ -81,6 +94,10 @@ inline bool pandas_number_prefix(const char* p, const char* end, double& out, co
   }
   if (p < end && *p == '.') {
     ++p;
+    uint64_t eight;
+    if (num_digits + 8 < exact_digits && end - p >= 8 && eight_digits(p, eight)) {   // the usual case: >= 8 decimals
+      acc = acc * 100000000ull + eight; num_digits += 8; num_decimals += 8; p += 8;
+    }
     while (num_digits < max_digits && p < end && is_digit(*p)) { push(*p - '0'); ++p; ++num_decimals; }
     if (num_digits >= max_digits) while (p < end && is_digit(*p)) ++p;
     exponent -= num_decimals;
