@@ -17,7 +17,8 @@ library exports (statistical, colors, shape, tde_physics, physics_based, bazin, 
              sample of the same workload, all host cores.
 * ``widened``  SURVEY 8(f) rows built so far, measured beside the step and not part of ``value`` (the 434-column
              table): the per-band 1-D GP pass (``extract_gp_features``, 21 columns) on a slice of the same batch, and
-             the native CSV ingest against the reference's pandas loading path on the box's host cores.
+             the native CSV ingest against the reference's pandas loading path on the box's host cores, and the
+             DataFrame-in / DataFrame-out call (``extract_feature_tables``) on the 10,178-object C1-shaped set.
 * ``--impl reference`` times only that CPU path (the reference has no GPU path and, being a Python
              package with no native code, "the reference's own CPU implementation" is the oracle
              restatement: ``/root/reference`` does not exist on the GPU box).
@@ -175,6 +176,27 @@ def ingest_rates(n_objects=2000):
         return {"error": f"{type(exc).__name__}: {exc}"}
     finally:
         shutil.rmtree(root, ignore_errors=True)
+
+
+def frames_e2e(n_objects=10178, device=0):
+    """The user-facing call itself on the C1-sized set (BASELINE.json configs[0] shape): the reference's long DataFrame in,
+    the reference's per-module DataFrames out (features.pipeline.extract_feature_tables = one K1 pack, the eight passes of
+    the 434-column table), host factorisation and DataFrame assembly included."""
+    try:
+        from mallorn_astrophysics_b200.features.pipeline import extract_feature_tables
+        from mallorn_astrophysics_b200.synth import make_table
+        tb = make_table(n_objects, config_index=1)
+        lc, meta, ids = tb.to_frame(), tb.metadata_frame(), list(tb.object_ids)
+        warm = ids[:512]
+        extract_feature_tables(lc[lc["object_id"].isin(set(warm))], meta, warm, modules=MODULES, device=device)
+        t0 = time.perf_counter()
+        tables = extract_feature_tables(lc, meta, ids, modules=MODULES, device=device)
+        dt = time.perf_counter() - t0
+        return {"call": "features.pipeline.extract_feature_tables(lightcurves, metadata, object_ids)", "objects": int(n_objects),
+                "rows": int(len(lc)), "seconds": dt, "objects_per_s": n_objects / dt,
+                "columns": int(sum(len(t.columns) - 1 for t in tables.values()))}
+    except Exception as exc:                                                # never lose the bench line over the side measurement
+        return {"error": f"{type(exc).__name__}: {exc}"}
 
 
 def run_reference_arm(args):
@@ -414,6 +436,7 @@ def run_gpu_arm(args):
                 widened["gp1d"]["cpu_baseline"] = {"value": rate_w, "unit": UNIT, "cores": cores, "kind": "port",
                                                    "sample": f"first {n_w} objects of the CPU sample, oracle/gp1d.py, {secs_w:.1f} s"}
                 widened["ingest"] = ingest_rates()
+                widened["frames_e2e"] = frames_e2e(device=local)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
