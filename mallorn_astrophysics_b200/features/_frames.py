@@ -21,15 +21,11 @@ def _request_index(ids, object_ids):
     return ids.get_indexer(pd.Series(list(object_ids), dtype=object))
 
 
-def run_frame_modules(modules: Sequence[str], lightcurves, object_ids: Optional[Sequence] = None, metadata=None,
-                      device: int = 0) -> dict:
-    """Pack once (K1), run every pass of ``modules`` on the same device-resident store, return ``{module: DataFrame}``
-    with the reference's per-module schema."""
+def frames_from_store(store, ids, object_ids: Sequence, modules: Sequence[str], metadata=None) -> dict:
+    """Run every pass of ``modules`` on a packed store whose dense object index follows ``ids`` and assemble the
+    reference's per-module DataFrames for the requested ``object_ids`` (request order, ids without observations omitted).
+    Closes the store."""
     import pandas as pd
-    if object_ids is None:
-        object_ids = lightcurves["object_id"].unique()
-    object_ids = list(object_ids)
-    store, ids = LightCurveStore.from_frame(lightcurves, object_ids, device=device)
     try:
         z = None
         if "physics" in modules or ("research" in modules and metadata is not None):
@@ -43,6 +39,7 @@ def run_frame_modules(modules: Sequence[str], lightcurves, object_ids: Optional[
     finally:
         store.close()
     req = _request_index(ids, object_ids)
+    req = req[req >= 0]                              # ids that are not in the store at all
     req = req[counts[req] > 0]                       # drop ids with no observations
     id_col = np.asarray(ids, dtype=object)[req]
     frames = {}
@@ -58,6 +55,39 @@ def run_frame_modules(modules: Sequence[str], lightcurves, object_ids: Optional[
             df["object_id"] = id_col
         frames[module] = df
     return frames
+
+
+def run_frame_modules(modules: Sequence[str], lightcurves, object_ids: Optional[Sequence] = None, metadata=None,
+                      device: int = 0) -> dict:
+    """Pack once (K1), run every pass of ``modules`` on the same device-resident store, return ``{module: DataFrame}``
+    with the reference's per-module schema."""
+    if object_ids is None:
+        object_ids = lightcurves["object_id"].unique()
+    object_ids = list(object_ids)
+    store, ids = LightCurveStore.from_frame(lightcurves, object_ids, device=device)
+    return frames_from_store(store, ids, object_ids, modules, metadata)
+
+
+def run_csv_modules(modules: Sequence[str], paths, object_ids: Optional[Sequence] = None, metadata=None, device: int = 0,
+                    threads: int = 0) -> dict:
+    """The same from light-curve CSV files (no DataFrame on the way in): native ingest -> K1 -> passes.  ``object_ids``
+    default: every object of the files, in order of first appearance."""
+    import pandas as pd
+    try:
+        from .. import ingest
+    except ImportError:                              # imported as top-level `features`
+        from mallorn_astrophysics_b200 import ingest
+    cols = ingest.read_lightcurve_csv(paths, threads)
+    if object_ids is None:
+        ids, obj = pd.Index(cols.object_ids), cols.obj
+        object_ids = list(cols.object_ids)
+    else:
+        object_ids = list(object_ids)
+        ids = pd.Index(pd.unique(pd.Series(object_ids, dtype=object)))
+        remap = np.append(ids.get_indexer(pd.Index(cols.object_ids)).astype(np.int32), np.int32(-1))   # file id -> request slot
+        obj = remap[cols.obj]                        # rows without an id (-1) pick the appended -1
+    store = LightCurveStore(obj, cols.band, cols.t, cols.flux, cols.err, len(ids), device=device)
+    return frames_from_store(store, ids, object_ids, modules, metadata)
 
 
 def run_frame_module(module: str, lightcurves, object_ids: Optional[Sequence] = None, metadata=None,

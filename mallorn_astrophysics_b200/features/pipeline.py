@@ -16,7 +16,7 @@ from typing import Dict, List, Optional, Sequence
 
 import pandas as pd
 
-from ._frames import run_frame_modules
+from ._frames import run_csv_modules, run_frame_modules
 
 ALL_MODULES = ("statistical", "colors", "shape", "physics", "tde", "bazin", "powerlaw", "gp2d", "gp1d")
 
@@ -33,3 +33,17 @@ def extract_feature_tables(lightcurves: pd.DataFrame, metadata: Optional[pd.Data
     if "physics" in modules and metadata is None:
         raise ValueError("the physics module needs the metadata frame (object_id, Z)")
     return run_frame_modules(modules, lightcurves, object_ids, metadata, device)
+
+
+def extract_feature_tables_from_csv(paths, metadata: Optional[pd.DataFrame] = None, object_ids: Optional[List[str]] = None,
+                                    modules: Sequence[str] = ALL_MODULES, device: int = 0, threads: int = 0) -> Dict[str, pd.DataFrame]:
+    """The same tables straight from light-curve CSV files (``split_XX/{train,test}_full_lightcurves.csv``): the native
+    reader (``ingest.read_lightcurve_csv``, bit-identical to ``pd.read_csv`` + ``pd.concat``) feeds K1 without building the
+    long DataFrame.  ``object_ids`` default: every object of the files in order of first appearance."""
+    modules = list(modules)
+    unknown = [m for m in modules if m not in ALL_MODULES]
+    if unknown:
+        raise KeyError(f"unknown feature module(s) {unknown}; known: {list(ALL_MODULES)}")
+    if "physics" in modules and metadata is None:
+        raise ValueError("the physics module needs the metadata frame (object_id, Z)")
+    return run_csv_modules(modules, paths, object_ids, metadata, device, threads)
