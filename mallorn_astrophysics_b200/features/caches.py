@@ -44,10 +44,41 @@ def merged_v4_table(tables: Dict[str, pd.DataFrame], metadata: pd.DataFrame) -> 
     return out
 
 
+def _split_files(data_path: Path, split: str):
+    files = [data_path / f"split_{i:02d}" / f"{split}_full_lightcurves.csv" for i in range(1, 21)]      # data_loader.py:49-57
+    files = [f for f in files if f.exists()]
+    if not files:
+        raise FileNotFoundError(f"No {split} lightcurve files found")
+    return files
+
+
+def write_feature_caches_from_files(data_path, out_dir, overwrite: bool = False, files: Sequence[str] = CACHE_FILES,
+                                    device: int = 0, threads: int = 0) -> Dict[str, Path]:
+    """``write_feature_caches`` from the raw data directory (``train_log.csv``, ``test_log.csv``, ``split_XX/*_full_lightcurves.csv``;
+    ``utils/data_loader.py:21-62``) without building the long DataFrames: the split files go through the native reader
+    straight into K1.  Same files, same structures."""
+    data_path = Path(data_path)
+    train_meta = pd.read_csv(data_path / "train_log.csv")                # data_loader.py:31-32
+    test_meta = pd.read_csv(data_path / "test_log.csv")
+    return _write(lambda mods: pipeline.extract_feature_tables_from_csv(_split_files(data_path, "train"), train_meta,
+                                                                        train_meta["object_id"].tolist(), modules=mods,
+                                                                        device=device, threads=threads),
+                  lambda mods: pipeline.extract_feature_tables_from_csv(_split_files(data_path, "test"), test_meta,
+                                                                        test_meta["object_id"].tolist(), modules=mods,
+                                                                        device=device, threads=threads),
+                  train_meta, test_meta, out_dir, overwrite, files)
+
+
 def write_feature_caches(train_lc: pd.DataFrame, train_meta: pd.DataFrame, test_lc: pd.DataFrame, test_meta: pd.DataFrame,
                          out_dir, overwrite: bool = False, files: Sequence[str] = CACHE_FILES, device: int = 0) -> Dict[str, Path]:
     """Write the cache files named in ``files`` (default: all seven) into ``out_dir``.  Returns ``{file name: path}`` of
     the files written by this call."""
+    return _write(lambda mods: pipeline.extract_feature_tables(train_lc, train_meta, train_meta["object_id"].tolist(), modules=mods, device=device),
+                  lambda mods: pipeline.extract_feature_tables(test_lc, test_meta, test_meta["object_id"].tolist(), modules=mods, device=device),
+                  train_meta, test_meta, out_dir, overwrite, files)
+
+
+def _write(run_train, run_test, train_meta, test_meta, out_dir, overwrite, files) -> Dict[str, Path]:
     unknown = [f for f in files if f not in CACHE_FILES]
     if unknown:
         raise KeyError(f"unknown cache file(s) {unknown}; known: {list(CACHE_FILES)}")
@@ -61,10 +92,8 @@ def write_feature_caches(train_lc: pd.DataFrame, train_meta: pd.DataFrame, test_
             "gp_features_cache.pkl": ("gp1d",), "powerlaw_features.pkl": ("powerlaw",)}
     test_modules = [m for m in pipeline.ALL_MODULES if any(m in need[f] for f in todo if f != "powerlaw_features.pkl")]
     train_modules = [m for m in pipeline.ALL_MODULES if any(m in need[f] for f in todo)]
-    train_ids = train_meta["object_id"].tolist()
-    test_ids = test_meta["object_id"].tolist()
-    train = pipeline.extract_feature_tables(train_lc, train_meta, train_ids, modules=train_modules, device=device)
-    test = pipeline.extract_feature_tables(test_lc, test_meta, test_ids, modules=test_modules, device=device) if test_modules else {}
+    train = run_train(train_modules)
+    test = run_test(test_modules) if test_modules else {}
     written = {}
 
     def dump(name, obj, how):

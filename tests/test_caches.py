@@ -98,3 +98,40 @@ def test_existing_caches_are_kept_and_subsets_run_only_what_they_need(fake_gpu, 
     assert list(w) == ["powerlaw_features.pkl"] and calls == [("train", ("powerlaw",))]
     with pytest.raises(KeyError):
         caches.write_feature_caches(*args, files=["nope.pkl"])
+
+
+def test_caches_from_raw_files_equal_caches_from_frames(tmp_path, monkeypatch):
+    """write_feature_caches_from_files (train_log.csv / test_log.csv / split_XX files -> native reader -> K1) against
+    write_feature_caches on the DataFrames pd.read_csv gives; the kernels are replaced by the oracle-backed store of
+    tests/test_frames_cpu.py, so this runs on the CPU."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_frames_cpu import OracleStore
+    from mallorn_astrophysics_b200.features import _frames
+    import __graft_entry__ as entry
+    entry.build()
+    monkeypatch.setattr(_frames, "LightCurveStore", OracleStore)
+    raw = tmp_path / "raw"
+    sets = {"train": make_table(10, seed=11), "test": make_table(7, seed=12)}
+    frames = {}
+    for split, tb in sets.items():
+        lc, meta = tb.to_frame(), tb.metadata_frame()
+        meta.to_csv(raw.mkdir(exist_ok=True) or raw / f"{split}_log.csv", index=False)
+        half = len(lc) // 2
+        for i, part in enumerate((lc.iloc[:half], lc.iloc[half:])):
+            d = raw / f"split_{i + 1:02d}"
+            d.mkdir(exist_ok=True)
+            part.to_csv(d / f"{split}_full_lightcurves.csv", index=False)
+        frames[split] = (pd.concat([pd.read_csv(raw / f"split_{i:02d}" / f"{split}_full_lightcurves.csv") for i in (1, 2)], ignore_index=True),
+                         pd.read_csv(raw / f"{split}_log.csv"))
+    which = ["features_v4_cache.pkl", "tde_physics_cache.pkl"]
+    a = caches.write_feature_caches_from_files(raw, tmp_path / "a", files=which)
+    b = caches.write_feature_caches(frames["train"][0], frames["train"][1], frames["test"][0], frames["test"][1], tmp_path / "b", files=which)
+    assert set(a) == set(b) == set(which)
+    for name in which:
+        da, db = pd.read_pickle(tmp_path / "a" / name), pd.read_pickle(tmp_path / "b" / name)
+        assert set(da) == set(db)
+        for k in da:
+            pd.testing.assert_frame_equal(da[k], db[k])
+    assert len(pd.read_pickle(tmp_path / "a" / "features_v4_cache.pkl")["train_features"]) == 10
