@@ -161,3 +161,43 @@ def test_number_grammar_adversarial_spellings(ingest, tmp_path):
     want = np.array([v for _, v in numeric])
     same = (got.view(np.uint64) == want.view(np.uint64)) | (np.isnan(got) & np.isnan(want))
     assert same.all(), [(numeric[i][0], got[i], want[i]) for i in np.flatnonzero(~same)[:5]]
+
+
+def test_malformed_files_are_rejected_or_parsed_never_crash(ingest, tmp_path):
+    """random bytes, truncated lines, CRLF, blank lines, absurdly long numbers, NULs, wrong headers: the native reader either
+    returns consistent columns or raises MallornIngestError"""
+    rng = np.random.default_rng(5)
+    hdr = b"object_id,Time (MJD),Flux,Flux_err,Filter\n"
+    good = [b"a,60000.5,1.25,0.5,g", b"bb,6e4,-3,1,r", b",1,2,3,z", b"c,1,,3,", b"d, 1 ,2,3,u"]
+    alphabet = list(b"0123456789.,-+eE \r\n\"abcNnaiIfF\t\x00\xff")
+    parsed = rejected = 0
+    for it in range(600):
+        mode = rng.integers(0, 8)
+        if mode == 0:
+            body = bytes(rng.choice(alphabet, rng.integers(0, 400)).tolist())
+        elif mode == 1:
+            body = b"\n".join(good[i] for i in rng.integers(0, len(good), rng.integers(0, 30)))
+        elif mode == 2:
+            body = b"\n".join(good[i] for i in rng.integers(0, len(good), 10))[:rng.integers(0, 150)]
+        elif mode == 3:
+            body = b"\r\n".join(good[i] for i in rng.integers(0, len(good), 10)) + b"\r\n\r\n"
+        elif mode == 4:
+            body = b"x," + b"9" * int(rng.integers(1, 5000)) + b",1e" + b"9" * int(rng.integers(1, 40)) + b",0." + b"0" * 400 + b"1,g\n"
+        elif mode == 5:
+            body = b"\n" * int(rng.integers(0, 50))
+        elif mode == 6:
+            body = b",".join([b"q"] * int(rng.integers(0, 12))) + b"\n" + good[0]
+        else:
+            body = bytes(rng.integers(0, 256, rng.integers(0, 300), dtype=np.uint8).tolist())
+        head = hdr if rng.random() < 0.85 else bytes(rng.choice(alphabet, rng.integers(0, 60)).tolist()) + b"\n"
+        p = tmp_path / "f.csv"
+        p.write_bytes(head + body)
+        try:
+            c = ingest.read_lightcurve_csv(p, threads=int(rng.integers(1, 5)))
+        except ingest.MallornIngestError:
+            rejected += 1
+            continue
+        parsed += 1
+        assert len(c.obj) == len(c.band) == len(c.t) == len(c.flux) == len(c.err)
+        assert (c.obj < len(c.object_ids)).all() and (c.obj >= -1).all() and (c.band <= 6).all()
+    assert parsed > 100 and rejected > 100
