@@ -13,9 +13,23 @@ namespace {
 // evaluation per trip, and a lane whose fit ends takes the next (object, band[, model]) from the
 // ticket counter, so the 100x spread in iteration counts does not idle the warp.
 // ------------------------------------------------------------------------------------------------
-constexpr int FIT_THREADS = 512;          // 8 warps that start every trip together (see the barrier in the loops)
+#ifndef FIT_THREADS_N
+#define FIT_THREADS_N 512
+#endif
+#ifndef FIT_MIN_BLOCKS
+#define FIT_MIN_BLOCKS 1
+#endif
+constexpr int FIT_THREADS = FIT_THREADS_N;     // warps of one CTA start every trip together (see the barrier in the loops)
+// true while any lane of the group (CTA, or warp in the barrier-free developer build) still has work
+__device__ __forceinline__ bool group_any(bool pred) {
+#ifdef FIT_NO_BARRIER
+  return __any_sync(0xffffffffu, pred);
+#else
+  return __syncthreads_or(pred);
+#endif
+}
 
-__global__ void __launch_bounds__(FIT_THREADS, 1)
+__global__ void __launch_bounds__(FIT_THREADS, FIT_MIN_BLOCKS)
 k_bazin_thread(const long long* __restrict__ seg_off, const double* __restrict__ gt, const double* __restrict__ gf,
                const double* __restrict__ ge, int n_obj, unsigned long long* __restrict__ ticket,
                double* __restrict__ out, int* __restrict__ status) {
@@ -37,7 +51,7 @@ k_bazin_thread(const long long* __restrict__ seg_off, const double* __restrict__
         if (status) { status[(o * N_BAND + b) * 2] = code; status[(o * N_BAND + b) * 2 + 1] = 0; }
       }
     }
-    if (!__syncthreads_or(active || !exhausted)) break;      // also lines the warps up: they fetch the same code
+    if (!group_any(active || !exhausted)) break;      // also lines the warps up: they fetch the same code
     if (active) {
       const int rc = job.step();
       if (rc != TRF_RUNNING) {
@@ -67,7 +81,7 @@ __global__ void k_bazin_tail(int n_obj, double* __restrict__ out) {
 
 // KIND 0: the seven fixed-index power laws (21 fits per object); 1: exponential; 2: linear (3 per object each)
 template <int KIND>
-__global__ void __launch_bounds__(FIT_THREADS, 1)
+__global__ void __launch_bounds__(FIT_THREADS, FIT_MIN_BLOCKS)
 k_decline_thread(const long long* __restrict__ seg_off, const double* __restrict__ gt, const double* __restrict__ gf,
                  int n_obj, unsigned long long* __restrict__ ticket, double* __restrict__ out, int* __restrict__ status) {
   constexpr int PER_BAND = (KIND == 0) ? 7 : 1;
@@ -98,7 +112,7 @@ k_decline_thread(const long long* __restrict__ seg_off, const double* __restrict
         if (status) { status[s * 2] = code; status[s * 2 + 1] = 0; }
       }
     }
-    if (!__syncthreads_or(active || !exhausted)) break;
+    if (!group_any(active || !exhausted)) break;
     if (active) {
       const int rc = job.step();
       if (rc != TRF_RUNNING) {
