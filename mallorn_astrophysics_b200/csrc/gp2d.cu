@@ -36,6 +36,14 @@ namespace {
 #endif
 constexpr int GP_THREADS = GP_THREADS_N;
 constexpr int GP_WARPS = GP_THREADS / 32;
+// Warp roles during a sweep step.  A scheduler partition owns the warps with the same (warp id % 4) and ONE FP64 pipe:
+// a DMMA occupies it for 16 cycles, so every dependent DFMA of the serial pivot chain queued behind the three bulk warps
+// of its partition (measured: 4.1 k cycles per pivot tile alone, 7.2-8.6 k beside them -- longer than the whole bulk
+// phase).  The pivot warp therefore gets its partition to itself while it factors: the other warps of partition 0 run the
+// small jobs and then wait for it, and the rank-16 tile updates go to the warps of partitions 1..3.
+constexpr int PIV = 0;
+static_assert(GP_WARPS >= 8 && GP_WARPS % 4 == 0, "the role split needs at least two warps per scheduler partition");
+constexpr int N_BULK = GP_WARPS - GP_WARPS / 4;
 constexpr int TB = 16;                 // tile edge
 constexpr int TT = TB * TB;            // doubles per tile
 constexpr int GP_COLS = 27;
@@ -66,6 +74,7 @@ struct GpShared {
   double *Lc, *Li, *LiT, *w;              // pivot factor; its inverse row-major / transposed (stride VLD); L^-1 b_k
   double *red, *bc;                     // reduction scratch, broadcast slots
   unsigned char *tI, *tJ;
+  int* flag;                            // = k+1 once pivot tile k+1 of the current evaluation is factored
 };
 
 __device__ __forceinline__ double* tile_ptr(const GpShared& S, int I, int J) { return S.tiles + (size_t)(I * (I + 1) / 2 + J) * TT; }
@@ -88,10 +97,19 @@ __device__ __forceinline__ KernelPars unpack(const double* p) {
   KernelPars k; k.mean = p[0]; k.amp = 2.0 * exp(p[1]); k.im0 = exp(-p[2]); k.im1 = exp(-p[3]); return k;   // amp = ndim * exp(log_constant)
 }
 
-// tile element (r, c): column-major with the row index XOR-swizzled by an even number, so that both a
-// column of the tile (r varies) and a row of it (c varies: the transposed reads of the sweep) spread
-// over the shared-memory banks, and (r, r+1) pairs with r even stay one aligned double2
-__device__ __forceinline__ int tix(int r, int c) { return c * TB + (r ^ (c & 14)); }
+// Tile element (r, c).  A tile is stored in the FRAGMENT ORDER of the FP64 tensor-core accumulator (mma.m8n8k4: lane l
+// of a warp holds C[l/4][2(l%4)] and C[l/4][2(l%4)+1] of an 8x8 quadrant): quadrant (r/8, c/8), then lane, then the pair.
+// The rank-16 update -- 45 of the 63 tile products of a sweep step -- then reads and writes its accumulators as four
+// conflict-free 128-bit accesses per lane; the column-major layout of round 1 cost eight 64-bit accesses with a 2-way
+// bank conflict each, and the sweep is bound by shared-memory bandwidth (8 KB of traffic per 4096-FMA tile product).
+__device__ __forceinline__ int tix(int r, int c) {
+  return ((((r >> 3) * 2 + (c >> 3)) * 32 + (r & 7) * 4 + ((c & 7) >> 1)) << 1) | (c & 1);
+}
+// inverse: storage index -> (r, c); consecutive threads then touch consecutive words
+__device__ __forceinline__ void tix_decode(int idx, int& r, int& c) {
+  r = ((idx >> 7) << 3) | ((idx >> 3) & 7);
+  c = (((idx >> 6) & 1) << 3) | (((idx >> 1) & 3) << 1) | (idx & 1);
+}
 
 // running product of the pivots as mantissa * 2^exponent (ln|K| is taken once per evaluation, off the critical path)
 struct LogDet {
@@ -105,6 +123,8 @@ struct LogDet {
 // ride on the SAME broadcasts: forward substitution of column j needs exactly L[c2][c] x_c, the term the
 // Cholesky update multiplies by L[r][c].  The right-hand side b_k is carried as one more value per row lane,
 // so w = L^-1 b_k also falls out of the same loop.  Results in S.Li / S.LiT / S.w [buf].
+// (A square-root-free LDL^T form with the reciprocal off the dependency chain was measured in round 2: 5.5 k cycles
+// per tile against 4.1 k for this one, both running alone -- the chain is not what bounds it.)
 __device__ __forceinline__ void pivot_warp(const GpShared& S, int k, int buf, double& quad, LogDet& logdet, int& fail) {
   const int lane = threadIdx.x & 31, r = lane & 15;
   const bool lower = lane < TB;
@@ -170,23 +190,20 @@ __device__ __forceinline__ void dmma_16x16x16(double (&acc)[2][2][2], const doub
   }
 }
 
-// C(i, j) -= Vi Vj^T        (C swizzled tile, V tiles k-major with stride VLD)
+// C(i, j) -= Vi Vj^T        (C in fragment order, V tiles k-major with stride VLD)
 __device__ __forceinline__ void tile_update(double* __restrict__ C, const double* __restrict__ Vi, const double* __restrict__ Vj) {
-  const int lane = threadIdx.x & 31, lr = lane >> 2, lc = 2 * (lane & 3);
+  const int lane = threadIdx.x & 31;
+  double2* __restrict__ C2 = reinterpret_cast<double2*>(C);
   double acc[2][2][2];
 #pragma unroll
   for (int ri = 0; ri < 2; ++ri)
 #pragma unroll
-    for (int ci = 0; ci < 2; ++ci)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) { const int r = 8 * ri + lr, c = 8 * ci + lc + e; acc[ri][ci][e] = C[tix(r, c)]; }
+    for (int ci = 0; ci < 2; ++ci) { const double2 v = C2[(ri * 2 + ci) * 32 + lane]; acc[ri][ci][0] = v.x; acc[ri][ci][1] = v.y; }
   dmma_16x16x16(acc, Vi, VLD, Vj, VLD, true);
 #pragma unroll
   for (int ri = 0; ri < 2; ++ri)
 #pragma unroll
-    for (int ci = 0; ci < 2; ++ci)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) { const int r = 8 * ri + lr, c = 8 * ci + lc + e; C[tix(r, c)] = acc[ri][ci][e]; }
+    for (int ci = 0; ci < 2; ++ci) C2[(ri * 2 + ci) * 32 + lane] = make_double2(acc[ri][ci][0], acc[ri][ci][1]);
 }
 
 // V = X Li^T, X = block (i, k) of the symmetric matrix: tile(i, k) if i > k, tile(k, i)^T if i < k.
@@ -222,15 +239,34 @@ __device__ __forceinline__ void tile_finalise(double* __restrict__ Tl, bool tran
   const int lane = threadIdx.x & 31, lr = lane >> 2, lc = 2 * (lane & 3);
   double acc[2][2][2] = {};
   dmma_16x16x16(acc, V, VLD, Li, TB, false);
+  if (!transposed) {
+    double2* T2 = reinterpret_cast<double2*>(Tl);
 #pragma unroll
-  for (int ri = 0; ri < 2; ++ri)
+    for (int ri = 0; ri < 2; ++ri)
 #pragma unroll
-    for (int ci = 0; ci < 2; ++ci)
+      for (int ci = 0; ci < 2; ++ci) T2[(ri * 2 + ci) * 32 + lane] = make_double2(acc[ri][ci][0], acc[ri][ci][1]);
+  } else {
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int r = 8 * ri + lr, c = 8 * ci + lc + e;
-        Tl[transposed ? tix(c, r) : tix(r, c)] = acc[ri][ci][e];
-      }
+    for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+      for (int ci = 0; ci < 2; ++ci)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) Tl[tix(8 * ci + lc + e, 8 * ri + lr)] = acc[ri][ci][e];
+  }
+}
+
+// One bulk task of sweep step k: a rank-16 update of a tile outside row/column k, or column k <- V_i Li.
+__device__ __forceinline__ void bulk_task(const GpShared& S, int task, int k, int nupd, const double* __restrict__ Li) {
+  if (task < nupd) {
+    const int ii = S.tI[task], jj = S.tJ[task];
+    const int i = ii + (ii >= k), j = jj + (jj >= k);
+    if (i == k + 1 && j == k + 1) return;             // the pivot warp's
+    tile_update(tile_ptr(S, i, j), S.vbuf + i * VT, S.vbuf + j * VT);
+  } else {
+    const int q = task - nupd, i = q + (q >= k);
+    if (i > k) tile_finalise(tile_ptr(S, i, k), false, S.vbuf + i * VT, Li);
+    else tile_finalise(tile_ptr(S, k, i), true, S.vbuf + i * VT, Li);
+  }
 }
 
 // -ln L and its gradient at p.  Leaves alpha in S.sb[0..n).  Result broadcast to every thread.
@@ -238,9 +274,16 @@ __device__ __forceinline__ void tile_finalise(double* __restrict__ Tl, bool tran
 // between the build and the gradient contraction.
 #ifdef GP_PHASE_TIMING
 __device__ unsigned long long g_gp_phase[12];     // developer build only: cycles per phase summed over CTA 0's evaluations
-#define GP_TICK(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd(&g_gp_phase[slot], (unsigned long long)(now_ - t_mark_)); t_mark_ = now_; } } while (0)
+#define GP_TICK(slot) do { if (blockIdx.x == 0 && threadIdx.x == PIV * 32) { const long long now_ = clock64(); atomicAdd(&g_gp_phase[slot], (unsigned long long)(now_ - t_mark_)); t_mark_ = now_; } } while (0)
+// per-warp split of the sweep (lane 0 of every warp of CTA 0): 0 task acquire, 1 tile updates, 2 column finalise, 3 small jobs,
+// 4 wait at the end-of-step barrier, 5 number of tile updates, 6 pivot-warp work (update + b + factor), 7 scale phase + its barrier
+__device__ unsigned long long g_gp_warp[GP_WARPS][8];
+#define GPW_ADD(kind) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) { const long long n_ = clock64(); atomicAdd(&g_gp_warp[threadIdx.x >> 5][kind], (unsigned long long)(n_ - gw_t_)); gw_t_ = n_; } } while (0)
+#define GPW_COUNT(kind) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) atomicAdd(&g_gp_warp[threadIdx.x >> 5][kind], 1ULL); } while (0)
 #else
 #define GP_TICK(slot) do { } while (0)
+#define GPW_ADD(kind) do { } while (0)
+#define GPW_COUNT(kind) do { } while (0)
 #endif
 
 __device__ __forceinline__ void gp_eval(const GpShared& S, double* __restrict__ cache, int n, int T, int T_cap,
@@ -254,8 +297,10 @@ __device__ __forceinline__ void gp_eval(const GpShared& S, double* __restrict__ 
   double* cache_s = cache;
   double* cache_e = cache + (size_t)n_tiles(T_cap) * TT;
   // ---- (a) kernel matrix, b = y - mean
-  for (int e = tid; e < nt * TT; e += GP_THREADS) {
-    const int tl = e >> 8, r = e & 15, c = (e >> 4) & 15;
+  for (int e = tid; e < nt * TT; e += GP_THREADS) {           // e = storage index: tile, then fragment order
+    const int tl = e >> 8;
+    int r, c;
+    tix_decode(e & 255, r, c);
     const int gi = S.tI[tl] * TB + r, gj = S.tJ[tl] * TB + c;
     double v;
     if (gi >= n || gj >= n) v = (gi == gj) ? 1.0 : 0.0;
@@ -267,32 +312,45 @@ __device__ __forceinline__ void gp_eval(const GpShared& S, double* __restrict__ 
       v = kp.amp * (1.0 + s) * ex;
       if (gi == gj) v += S.sn[gi];
     }
-    S.tiles[tl * TT + tix(r, c)] = v;
+    S.tiles[e] = v;
   }
   for (int i = tid; i < T * TB; i += GP_THREADS) S.sb[i] = (i < n) ? S.sy[i] - kp.mean : 0.0;
-  double quad = 0.0; LogDet logdet{1.0, 0}; int fail = 0;     // accumulated by warp 0 (uniform across its lanes)
+  double quad = 0.0; LogDet logdet{1.0, 0}; int fail = 0;     // accumulated by the pivot warp (uniform across its lanes)
   __syncthreads();
   GP_TICK(0);
+#ifdef GP_PHASE_TIMING
+  if (blockIdx.x == 0 && tid == PIV * 32) { atomicAdd(&g_gp_phase[10], 1ULL); atomicAdd(&g_gp_phase[11], (unsigned long long)T); }
+#endif
   // ---- (b) tile sweep with look-ahead: warp 0 owns the critical path (next pivot tile), warps 1.. the bulk
-  if (warp == 0) pivot_warp(S, 0, 0, quad, logdet, fail);
+  if (warp == PIV) pivot_warp(S, 0, 0, quad, logdet, fail);
   __syncthreads();
   GP_TICK(1);
+#ifdef GP_PHASE_TIMING
+  long long gw_t_ = clock64();
+#endif
+  if (tid == 0) *S.flag = 0;                           // (published by the barrier above the first step's helpers)
   for (int k = 0; k < T; ++k) {
     const int cur = k & 1, nxt = cur ^ 1;
     const double* Li = S.Li + cur * TT;
     const double* LiT = S.LiT + cur * VT;
     const double* wv = S.w + cur * TB;
-    // V_i = X_i Li^T for i != k: one warp per tile row
-    for (int q = warp; q < T - 1; q += GP_WARPS) {
-      const int i = q + (q >= k);
-      if (i > k) tile_scale(S.vbuf + i * VT, tile_ptr(S, i, k), false, LiT);
-      else tile_scale(S.vbuf + i * VT, tile_ptr(S, k, i), true, LiT);
-    }
-    __syncthreads();
-    GP_TICK(2);
-    if (warp == 0) {
-      if (k + 1 < T) {                                // finish row k+1 of this step first, then factor it
+    const bool has_next = k + 1 < T;
+    const int Tm = T - 1, nupd = Tm * (Tm + 1) / 2, ntask = nupd + Tm;
+    // Bulk tasks (rank-16 tile updates outside row/column k, then column k <- V_i Li) are dealt round-robin to the warps of
+    // partitions 1..3; the tail of the last, partly filled round goes to the other warps of partition 0, which run it once
+    // the next pivot tile is factored.
+    const int n_help = has_next ? ((ntask % N_BULK) < GP_WARPS / 4 - 1 ? (ntask % N_BULK) : GP_WARPS / 4 - 1) : 0;
+    // ---- phase A: V_i = X_i Li^T for i != k, one warp per tile row.  The pivot warp takes row k+1 and then runs AHEAD
+    // of the barrier (it only arrives): the update of tile (k+1, k+1), of b_{k+1} and the factorisation need V_{k+1} only.
+    if (warp == PIV) {
+      if (has_next) tile_scale(S.vbuf + (k + 1) * VT, tile_ptr(S, k + 1, k), false, LiT);
+      __threadfence_block();
+      asm volatile("bar.arrive 1, %0;" ::"r"(GP_THREADS) : "memory");
+      GP_TICK(2);
+      GPW_ADD(7);
+      if (has_next) {
         const double* V = S.vbuf + (k + 1) * VT;
+        __syncwarp();
         tile_update(tile_ptr(S, k + 1, k + 1), V, V);
         {                                             // b_{k+1} -= V_{k+1} w_k, the 16-term sums split over the two half-warps
           const int rr = lane & 15, m0 = (lane >> 4) * 8;
@@ -305,70 +363,83 @@ __device__ __forceinline__ void gp_eval(const GpShared& S, double* __restrict__ 
         __syncwarp();
         GP_TICK(3);
         pivot_warp(S, k + 1, nxt, quad, logdet, fail);
+        __threadfence_block();
+        if (lane == 0) *(volatile int*)S.flag = k + 1;
+        GP_TICK(6);
+        GPW_ADD(6);
       }
-      GP_TICK(6);
     } else {
-      // warp tasks: rank-16 updates of every tile outside row/column k ((k+1, k+1) belongs to warp 0),
-      // then column k <- V_i Li.  Disjoint tiles, so no ordering between them.
-      const int Tm = T - 1, nupd = Tm * (Tm + 1) / 2;
-      for (int task = warp - 1; task < nupd + Tm; task += GP_WARPS - 1) {
-        if (task < nupd) {
-          int ii = (int)((sqrt(8.0 * task + 1.0) - 1.0) * 0.5);
-          while (ii * (ii + 1) / 2 > task) --ii;
-          while ((ii + 1) * (ii + 2) / 2 <= task) ++ii;
-          const int jj = task - ii * (ii + 1) / 2;
-          const int i = ii + (ii >= k), j = jj + (jj >= k);
-          if (i == k + 1 && j == k + 1) continue;
-#ifdef GP_PHASE_TIMING
-          const long long tu0_ = clock64();
-#endif
-          tile_update(tile_ptr(S, i, j), S.vbuf + i * VT, S.vbuf + j * VT);
-#ifdef GP_PHASE_TIMING
-          if (blockIdx.x == 0 && tid == 32) { atomicAdd(&g_gp_phase[8], (unsigned long long)(clock64() - tu0_)); atomicAdd(&g_gp_phase[9], 1ULL); }
-#endif
-        } else {
-          const int q = task - nupd, i = q + (q >= k);
-          if (i > k) tile_finalise(tile_ptr(S, i, k), false, S.vbuf + i * VT, Li);
-          else tile_finalise(tile_ptr(S, k, i), true, S.vbuf + i * VT, Li);
-        }
+      for (int q = warp - 1; q < T - 1; q += GP_WARPS - 1) {
+        if (q == k) continue;                         // row k+1: the pivot warp's
+        const int i = q + (q >= k);
+        if (i > k) tile_scale(S.vbuf + i * VT, tile_ptr(S, i, k), false, LiT);
+        else tile_scale(S.vbuf + i * VT, tile_ptr(S, k, i), true, LiT);
       }
-      // pivot tile <- -(Li^T Li); b_i -= V_i w
-      const int t2 = tid - 32, nth = GP_THREADS - 32;
-      for (int e = t2; e < TT; e += nth) {
-        const int r = e & 15, c = e >> 4;
-        double s = 0.0;
-        for (int m = (r > c ? r : c); m < TB; ++m) s += Li[m * TB + r] * Li[m * TB + c];
-        tile_ptr(S, k, k)[tix(r, c)] = -s;
-      }
-      if (t2 < TB) {                                  // b_k <- Li^T w (nobody reads b_k or w_k any more in this step)
-        double s = 0.0;
-        for (int m = t2; m < TB; ++m) s += Li[m * TB + t2] * wv[m];
-        S.sb[k * TB + t2] = s;
-      }
-      for (int i = t2; i < T * TB; i += nth) {
-        const int ti = i >> 4, r = i & 15;
-        if (ti != k && ti != k + 1) {
-          const double* V = S.vbuf + ti * VT;
+      asm volatile("bar.sync 1, %0;" ::"r"(GP_THREADS) : "memory");
+      GPW_ADD(7);
+    }
+    // ---- phase B
+    if ((warp & 3) != 0) {
+      const int bulk_id = (warp >> 2) * 3 + (warp & 3) - 1;
+      for (int task = bulk_id; task < ntask - n_help; task += N_BULK) bulk_task(S, task, k, nupd, Li);
+      GPW_ADD(1);
+    } else {
+      if (warp == 4) {
+        // pivot tile <- -(Li^T Li) as one 16x16x16 product; b_k <- Li^T w (nobody reads b_k or w_k any more in this
+        // step); b_i -= V_i w for the rows outside tiles k and k+1
+        double acc[2][2][2] = {};
+        dmma_16x16x16(acc, Li, TB, Li, TB, false);
+        double2* P2 = reinterpret_cast<double2*>(tile_ptr(S, k, k));
+#pragma unroll
+        for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+          for (int ci = 0; ci < 2; ++ci) P2[(ri * 2 + ci) * 32 + lane] = make_double2(-acc[ri][ci][0], -acc[ri][ci][1]);
+        if (lane < TB) {
           double s = 0.0;
-          for (int m = 0; m < TB; ++m) s += V[m * VLD + r] * wv[m];
-          S.sb[i] -= s;
+          for (int m = lane; m < TB; ++m) s += Li[m * TB + lane] * wv[m];
+          S.sb[k * TB + lane] = s;
         }
+        double wreg[TB];
+#pragma unroll
+        for (int m = 0; m < TB; ++m) wreg[m] = wv[m];
+        for (int i = lane; i < T * TB; i += 32) {
+          const int ti = i >> 4, r = i & 15;
+          if (ti != k && ti != k + 1) {
+            const double* V = S.vbuf + ti * VT;
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int m = 0; m < TB; m += 2) { s0 += V[m * VLD + r] * wreg[m]; s1 += V[(m + 1) * VLD + r] * wreg[m + 1]; }
+            S.sb[i] -= s0 + s1;
+          }
+        }
+        GPW_ADD(3);
+      }
+      const int h = (warp >> 2) - 1;                  // the pivot warp (-1) is the critical path: it takes none
+      if (h >= 0 && h < n_help) {
+        if (lane == 0) while (*(volatile int*)S.flag != k + 1) __nanosleep(64);
+        __syncwarp();
+        GPW_ADD(0);
+        bulk_task(S, ntask - n_help + h, k, nupd, Li);
+        GPW_ADD(2);
       }
     }
     __syncthreads();
     GP_TICK(4);
+    GPW_ADD(4);
   }
   __syncthreads();
   // ---- (c) gradient contraction: 1/2 sum (alpha_i alpha_j - Kinv_ij) dK_ij ; tiles hold -Kinv
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
   for (int i = tid; i < n; i += GP_THREADS) acc[0] += S.sb[i];
   for (int e = tid; e < nt * TT; e += GP_THREADS) {
-    const int tl = e >> 8, r = e & 15, c = (e >> 4) & 15;
+    const int tl = e >> 8;
+    int r, c;
+    tix_decode(e & 255, r, c);
     const int I = S.tI[tl], J = S.tJ[tl];
     const int gi = I * TB + r, gj = J * TB + c;
     if (gi < n && gj < n) {
       const double wgt = (I == J) ? 1.0 : 2.0;
-      const double Aij = wgt * (S.sb[gi] * S.sb[gj] + S.tiles[tl * TT + tix(r, c)]);
+      const double Aij = wgt * (S.sb[gi] * S.sb[gj] + S.tiles[e]);
       const double dt = S.st[gi] - S.st[gj], dl = S.sl[gi] - S.sl[gj];
       const double a0 = dt * dt * kp.im0, a1 = dl * dl * kp.im1;
       const double s = cache_s[e], ex = cache_e[e];
@@ -377,7 +448,7 @@ __device__ __forceinline__ void gp_eval(const GpShared& S, double* __restrict__ 
     }
   }
   GP_TICK(5);
-  if (tid == 0) { S.bc[0] = quad; S.bc[1] = logdet.value(); S.bc[2] = (double)fail; }
+  if (tid == PIV * 32) { S.bc[0] = quad; S.bc[1] = logdet.value(); S.bc[2] = (double)fail; }
   block_sum4(S, acc);                                 // contains the barriers that publish bc[]
   const double ll = -0.5 * S.bc[0] - 0.5 * S.bc[1] - 0.5 * (double)n * LOG_2PI;
   if (S.bc[2] != 0.0 || !is_finite(ll)) {             // multiband_gp.py:141-154: 1e25 and a zero gradient
@@ -400,6 +471,7 @@ k_gp2d(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
   __shared__ int s_pk;
   __shared__ int s_go;
   __shared__ Lbfgs4 s_opt;              // optimiser state: advanced by thread 0, x broadcast to the CTA
+  __shared__ int s_flag;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int np_cap = T_cap * TB;
   GpShared S;
@@ -413,6 +485,7 @@ k_gp2d(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
     if (SMEM_TILES) { S.tiles = d; d += (size_t)n_tiles(T_cap) * TT; }
     else S.tiles = gscratch + (size_t)blockIdx.x * n_tiles(T_cap) * TT;
     S.tI = (unsigned char*)d; S.tJ = S.tI + n_tiles(T_cap);
+    S.flag = &s_flag;
     // address-space hints: everything carved from the dynamic shared array is shared memory
     __builtin_assume(__isShared(S.st)); __builtin_assume(__isShared(S.sl)); __builtin_assume(__isShared(S.sy));
     __builtin_assume(__isShared(S.sn)); __builtin_assume(__isShared(S.sb)); __builtin_assume(__isShared(S.Lc));
@@ -591,6 +664,11 @@ k_gp2d(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
 }  // namespace
 
 #ifdef GP_PHASE_TIMING
+extern "C" void mlrn_gp_warp_cycles(unsigned long long* out, int reset) {       // [GP_WARPS][8]
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_gp_warp, sizeof(unsigned long long) * GP_WARPS * 8);
+  if (reset) { unsigned long long z[GP_WARPS * 8] = {0}; cudaMemcpyToSymbol(g_gp_warp, z, sizeof(z)); }
+}
 extern "C" void mlrn_gp_phase_cycles(unsigned long long* out8, int reset) {
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(out8, g_gp_phase, sizeof(unsigned long long) * 12);

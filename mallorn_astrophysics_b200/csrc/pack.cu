@@ -329,8 +329,10 @@ int pack_device(mlrn_store* s, int64_t n_rows, const int32_t* obj, const uint8_t
   MLRN_CUDA(cudaMalloc(&s->rank, sizeof(unsigned short) * nr));
   MLRN_CUDA(cudaMalloc(&s->trank, sizeof(unsigned short) * nr));
   MLRN_CUDA(cudaMallocAsync(&rowid, sizeof(int) * nr, st));
-  if (n_rows > 0 && n_obj > 0) {
-    k_scatter<<<row_grid > 0 ? row_grid : 1, 256, 0, st>>>(obj, n_rows, n_obj, s->seg_off, cursor, rowid);
+  if (n_obj > 0) {
+    // k_arrange is the only writer of seg_meta, so it also runs for a batch without rows (every object then gets
+    // the count-0 / position -1 pattern and no input column is touched)
+    if (n_rows > 0) k_scatter<<<row_grid > 0 ? row_grid : 1, 256, 0, st>>>(obj, n_rows, n_obj, s->seg_off, cursor, rowid);
     const int np = next_pow2(s->max_obs > 1 ? s->max_obs : 1);
     const size_t smem = arrange_bytes_per_warp(np) * ARR_WARPS;
     MLRN_CUDA(cudaFuncSetAttribute(k_arrange, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -18,7 +18,7 @@ import pandas as pd
 
 from ._frames import run_csv_modules, run_frame_modules
 
-ALL_MODULES = ("statistical", "colors", "shape", "physics", "tde", "bazin", "powerlaw", "gp2d", "gp1d")
+ALL_MODULES = ("statistical", "colors", "shape", "physics", "tde", "bazin", "powerlaw", "gp2d", "gp1d", "research")
 
 
 def extract_feature_tables(lightcurves: pd.DataFrame, metadata: Optional[pd.DataFrame] = None,
@@ -30,7 +30,7 @@ def extract_feature_tables(lightcurves: pd.DataFrame, metadata: Optional[pd.Data
     unknown = [m for m in modules if m not in ALL_MODULES]
     if unknown:
         raise KeyError(f"unknown feature module(s) {unknown}; known: {list(ALL_MODULES)}")
-    if "physics" in modules and metadata is None:
+    if ("physics" in modules) and metadata is None:
         raise ValueError("the physics module needs the metadata frame (object_id, Z)")
     return run_frame_modules(modules, lightcurves, object_ids, metadata, device)
 
@@ -44,6 +44,6 @@ def extract_feature_tables_from_csv(paths, metadata: Optional[pd.DataFrame] = No
     unknown = [m for m in modules if m not in ALL_MODULES]
     if unknown:
         raise KeyError(f"unknown feature module(s) {unknown}; known: {list(ALL_MODULES)}")
-    if "physics" in modules and metadata is None:
+    if ("physics" in modules) and metadata is None:
         raise ValueError("the physics module needs the metadata frame (object_id, Z)")
     return run_csv_modules(modules, paths, object_ids, metadata, device, threads)

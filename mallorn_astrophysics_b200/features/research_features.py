@@ -1,9 +1,9 @@
-"""Drop-in for the reference's ``src/features/research_features.py`` (v115c block) -- EXPERIMENTAL.
+"""Drop-in for the reference's ``src/features/research_features.py`` (v115c block).
 
 ``extract_research_features(lightcurves, object_ids, metadata_df=None, verbose=True)`` keeps the reference signature
 (research_features.py:566; note the argument order: ids before the metadata frame) and the 40 column names.  The
-arithmetic (``csrc/research.cuh``) is verified against the reference on the CPU; the CUDA pass (``csrc/research.cu``) has
-not been validated on a GPU yet, so this module is not part of ``features.pipeline.ALL_MODULES`` or the cache driver.
+arithmetic (``csrc/research.cuh``) is held to the reference's own frames on the CPU (host instantiation) and on the B200
+(``tests/test_gpu_research.py``); the pass is part of ``features.pipeline.ALL_MODULES``.
 Redshifts come from ``metadata_df['Z']``; without a metadata frame (or for ``Z <= 0`` / missing ids) the five luminosity
 columns are NaN, as upstream (:553-560).
 """

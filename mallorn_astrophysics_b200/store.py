@@ -32,6 +32,26 @@ def _ptr(x, dtype):
     return a.ctypes.data, a, False
 
 
+def _out_ptr(x, dtype, shape, device: int, what: str):
+    """(address, on_device) of an OUTPUT buffer.  Outputs are never converted or copied: anything but a C-contiguous
+    array / tensor of exactly this dtype and shape (and, for CUDA tensors, on the store's device) is an error,
+    because the kernel would otherwise fill a temporary and leave the caller's buffer unwritten."""
+    shape = tuple(int(v) for v in shape)
+    if _is_torch(x):
+        import torch
+        want = {np.int32: torch.int32, np.float64: torch.float64}[dtype]
+        if x.dtype != want or not x.is_contiguous() or tuple(x.shape) != shape:
+            raise ValueError(f"{what} must be a contiguous {want} tensor of shape {shape}, got {x.dtype} {tuple(x.shape)}"
+                             f"{'' if x.is_contiguous() else ' (non-contiguous)'}")
+        if x.is_cuda and x.device.index != device:
+            raise ValueError(f"{what} lives on cuda:{x.device.index}, the store on cuda:{device}")
+        return x.data_ptr(), x.is_cuda
+    if not isinstance(x, np.ndarray) or x.dtype != np.dtype(dtype) or not x.flags.c_contiguous or x.shape != shape \
+            or not x.flags.writeable:
+        raise ValueError(f"{what} must be a writeable C-contiguous {np.dtype(dtype)} array of shape {shape}")
+    return x.ctypes.data, False
+
+
 def frame_columns(lightcurves, object_ids: Optional[Sequence] = None):
     """Host ingest: reference-format long DataFrame -> the flat columns K1 takes.
 
@@ -140,9 +160,18 @@ class LightCurveStore:
         ret = None
         if out is None:
             out = ret = np.empty((self.n_obj, cols), dtype=np.float64)
-        optr, okeep, odev = _ptr(out, np.float64)
-        if not _is_torch(out) and okeep is not out:
-            raise ValueError("out must be a C-contiguous float64 array")
+        optr, odev = _out_ptr(out, np.float64, (self.n_obj, cols), self.device, "out")
+        scols = {"bazin": 12, "powerlaw": 54, "gp2d": 4, "gp1d": 12}.get(module)
+        sptr = 0
+        if status is not None:
+            if scols is None:
+                raise ValueError(f"the '{module}' pass has no status table")
+            n_stat = int(status.numel() if _is_torch(status) else status.size)
+            if n_stat != self.n_obj * scols:
+                raise ValueError(f"status must hold {scols} int32 values per object ({self.n_obj * scols}), got {n_stat}")
+            sptr, sdev = _out_ptr(status, np.int32, tuple(status.shape), self.device, "status")
+            if sdev != odev:
+                raise ValueError("status and out must live on the same side")
         if module in ("physics", "research"):
             if z is None:
                 z = np.full(self.n_obj, np.nan)
@@ -150,16 +179,6 @@ class LightCurveStore:
             fn = L.mlrn_physics if module == "physics" else L.mlrn_research
             rc = fn(self._h, zptr, 1 if zdev else 0, optr, 1 if odev else 0, st)
         elif module in ("bazin", "powerlaw", "gp2d", "gp1d"):
-            sptr = 0
-            if status is not None:
-                if _is_torch(status):
-                    if status.is_cuda != odev:
-                        raise ValueError("status and out must live on the same side")
-                    sptr = status.data_ptr()
-                else:
-                    if odev or status.dtype != np.int32 or not status.flags.c_contiguous:
-                        raise ValueError("status must be a C-contiguous int32 array on the same side as out")
-                    sptr = status.ctypes.data
             fn = getattr(L, {"bazin": "mlrn_bazin", "powerlaw": "mlrn_powerlaw", "gp2d": "mlrn_gp2d",
                               "gp1d": "mlrn_gp1d"}[module])
             rc = fn(self._h, optr, sptr, 1 if odev else 0, st)

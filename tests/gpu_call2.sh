@@ -1,0 +1,7 @@
+#!/bin/bash
+set -x
+timeout 600 python -m pytest tests/test_gpu_gp2d.py -m gpu -q -x
+timeout 200 python tests/gpu_rate.py gp2d 100000 2
+MLRN_LIB=$PWD/variants/lib_gpchol.so timeout 200 python tests/gpu_rate.py gp2d 100000 2
+MLRN_LIB=$PWD/variants/lib_gpstatic.so timeout 200 python tests/gpu_rate.py gp2d 100000 2
+MLRN_LIB=$PWD/variants/lib_gpphase.so timeout 200 python tests/gpu_gp_phases.py 3000

@@ -128,6 +128,47 @@ def test_empty_and_degenerate_inputs():
     assert st[1, 122] == 2 and st[0, 122] == -1
 
 
+def test_requested_objects_without_any_row():
+    """An empty light-curve frame with requested ids (n_rows == 0, n_obj > 0): every segment count is 0, peak positions
+    are -1, no object is present, and the passes return rows for it (NaN / n_obs 0) instead of reading garbage."""
+    from mallorn_astrophysics_b200.store import LightCurveStore
+    e = np.empty(0)
+    with LightCurveStore(np.empty(0, np.int32), np.empty(0, np.uint8), e, e, e, 5) as s:
+        assert s.n_rows == 0 and s.n_obj == 5
+        seg = s.segments()
+        assert s.present().size == 0
+        st = s.features("statistical")
+        bz = s.features("bazin")
+    assert (seg[:, 0:21:3] == 0).all() and (seg[:, 1:21:3] == -1).all() and (seg[:, 2:21:3] == -1).all() and (seg[:, 21] == -1).all()
+    assert (st[:, 0:7 * 17:17] == 0).all() and np.isnan(st[:, 1]).all() and np.isnan(bz).all()
+
+
+def test_output_buffers_must_match_exactly():
+    """Outputs are never converted: a column slice of a wider table, a wrong dtype, shape or side raises instead of
+    filling a temporary."""
+    import torch
+    from mallorn_astrophysics_b200.store import LightCurveStore
+    from mallorn_astrophysics_b200.synth import make_table
+    table = make_table(8, seed=5)
+    with LightCurveStore.from_table(table) as s:
+        wide = torch.zeros((8, 200), dtype=torch.float64, device="cuda")
+        with pytest.raises(ValueError):
+            s.features("statistical", out=wide[:, :123])
+        with pytest.raises(ValueError):
+            s.features("statistical", out=torch.zeros((8, 123), dtype=torch.float32, device="cuda"))
+        with pytest.raises(ValueError):
+            s.features("statistical", out=np.zeros((7, 123)))
+        with pytest.raises(ValueError):
+            s.features("bazin", out=torch.zeros((8, 52), dtype=torch.float64, device="cuda"), status=np.zeros((8, 12), np.int32))
+        with pytest.raises(ValueError):
+            s.features("bazin", status=np.zeros((8, 11), np.int32))
+        assert (wide == 0).all()
+        good = torch.zeros((8, 123), dtype=torch.float64, device="cuda")
+        s.features("statistical", out=good)
+        torch.cuda.synchronize()
+        assert np.array_equal(good.cpu().numpy(), s.features("statistical"), equal_nan=True)
+
+
 def test_object_above_cap_is_rejected():
     from mallorn_astrophysics_b200 import _native
     from mallorn_astrophysics_b200.store import LightCurveStore

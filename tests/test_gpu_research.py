@@ -1,15 +1,10 @@
-"""GPU parity of the experimental K8 pass ("research" block, 40 columns; reference src/features/research_features.py)
-against the reference's own frames (tests/golden/*.npz: research_rows).  The arithmetic is the template that
-tests/test_hostsim.py already holds to these goldens on the CPU; this file is the first thing to run when GPU time is
-available again -- until then it is gated so that the default GPU suite only contains validated passes."""
-import os
-
+"""GPU parity of the K8 pass ("research" block, 40 columns; reference src/features/research_features.py) against the
+reference's own frames (tests/golden/*.npz: research_rows).  The arithmetic is the template that tests/test_hostsim.py
+holds to these goldens on the CPU."""
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MLRN_TEST_EXPERIMENTAL") != "1",
-                                 reason="mlrn_research has not been validated on a GPU yet; set MLRN_TEST_EXPERIMENTAL=1 to run it")]
+pytestmark = pytest.mark.gpu
 
 TIE_OBJECT = 15
 
