@@ -1,5 +1,17 @@
-// fits.cu -- K4 kernels: Bazin (52 columns) and decline-model (27 columns) passes, one thread per fit.
+// fits.cu -- K4 kernels: Bazin (52 columns) and decline-model (27 columns) passes, one thread per fit, run in STAGES.
+//
+// One THREAD per fit (trf_thread.cuh): every lane of a warp advances its own fit by one trial evaluation per trip, and a
+// lane whose fit ends takes the next (object, band[, model]) from a ticket counter.  Function-evaluation counts spread
+// 100x (median 34, mean 58, 1 % above 480, max_nfev = 2000), and a trip of a warp costs the union of its lanes' paths,
+// so a fit that runs long after the ticket counter is exhausted keeps a whole warp -- and, through the CTA-wide trip
+// barrier, a whole SM -- busy for one useful lane.  Round 1 measured that tail at 0.44 s per launch whatever the batch
+// size (11 % of a 10^6-object launch, 90 % of a 20,000-object one).  A stage therefore only runs a fit up to a cap of
+// function evaluations; a fit that is still running at the cap is written out whole (the solver is a resumable state
+// machine, so the job struct is the complete state) and picked up by the next stage, which has a higher cap, far fewer
+// fits, and -- once the survivors are fewer than the lanes -- spreads them one per warp, so that the stragglers no longer
+// pay for each other's divergence.  Caps double from stage to stage; the last stage has none.
 #include <cuda_runtime.h>
+#include <limits.h>
 #include "store.cuh"
 #include "fits.cuh"
 #include "fits_thread.cuh"
@@ -8,57 +20,117 @@
 namespace mlrn {
 namespace {
 
-// ------------------------------------------------------------------------------------------------
-// One THREAD per fit (trf_thread.cuh): every lane of a warp advances its own fit by one trial
-// evaluation per trip, and a lane whose fit ends takes the next (object, band[, model]) from the
-// ticket counter, so the 100x spread in iteration counts does not idle the warp.
-// ------------------------------------------------------------------------------------------------
 #ifndef FIT_THREADS_N
 #define FIT_THREADS_N 512
 #endif
 #ifndef FIT_MIN_BLOCKS
 #define FIT_MIN_BLOCKS 1
 #endif
-constexpr int FIT_THREADS = FIT_THREADS_N;     // warps of one CTA start every trip together (see the barrier in the loops)
-// true while any lane of the group (CTA, or warp in the barrier-free developer build) still has work
-__device__ __forceinline__ bool group_any(bool pred) {
-#ifdef FIT_NO_BARRIER
-  return __any_sync(0xffffffffu, pred);
-#else
-  return __syncthreads_or(pred);
-#endif
-}
+constexpr int FIT_THREADS = FIT_THREADS_N;     // warps of one CTA start every trip together (see the barrier in the loop)
+constexpr int MAX_STAGES = 6;
 
-__global__ void __launch_bounds__(FIT_THREADS, FIT_MIN_BLOCKS)
-k_bazin_thread(const long long* __restrict__ seg_off, const double* __restrict__ gt, const double* __restrict__ gf,
-               const double* __restrict__ ge, int n_obj, unsigned long long* __restrict__ ticket,
-               double* __restrict__ out, int* __restrict__ status) {
-  const long long total = (long long)n_obj * N_BAND;
-  BazinJob job;
-  bool active = false, exhausted = false;
+// a fit that outlived its stage: the whole resumable job and which fit it is
+template <class Job> struct FitCarry { Job job; long long fit; };
+
+struct StageIo {
+  unsigned long long* ticket;        // this stage's work counter
+  int cap;                           // function evaluations after which a running fit moves on (INT_MAX: never)
+  const void* in; const unsigned* in_count; unsigned in_capacity;       // carried fits to resume (nullptr: fresh fits)
+  void* out; unsigned* out_count; unsigned out_capacity;                // where survivors go (nullptr: last stage)
+};
+
+// ---- Bazin: fit = band * n_obj + object (band-major: the lanes of a warp get bands of similar length)
+struct BazinPolicy {
+  using Job = BazinJob;
+  const long long* seg_off; const double *gt, *gf, *ge; int n_obj; double* out; int* status;
+  __device__ long long total() const { return (long long)n_obj * N_BAND; }
+  __device__ bool start(Job& job, long long fit) const {
+    const int b = (int)(fit / n_obj); const long long o = fit % n_obj;
+    const long long lo = seg_off[o * N_SEG + b];
+    const int n = (int)(seg_off[o * N_SEG + b + 1] - lo);
+    int code;
+    if (job.init(gt + lo, gf + lo, ge + lo, n, code)) return true;
+    job.finish(code, out + o * BAZIN_COLS + 8 * b);
+    if (status) { status[(o * N_BAND + b) * 2] = code; status[(o * N_BAND + b) * 2 + 1] = 0; }
+    return false;
+  }
+  __device__ void done(const Job& job, long long fit, int rc) const {
+    const int b = (int)(fit / n_obj); const long long o = fit % n_obj;
+    job.finish(rc, out + o * BAZIN_COLS + 8 * b);
+    if (status) { status[(o * N_BAND + b) * 2] = rc; status[(o * N_BAND + b) * 2 + 1] = job.trf.nfev; }
+  }
+};
+
+// ---- decline models.  KIND 0: the seven fixed-index power laws (21 fits per object); 1: exponential; 2: linear (3 per
+// object each); (band, model)-major fit order: the lanes of a warp fit the same model to the same band of different objects
+template <int KIND>
+struct DeclinePolicy {
+  using Job = DeclineJob<KIND>;
+  static constexpr int PER_BAND = (KIND == 0) ? 7 : 1;
+  const long long* seg_off; const double *gt, *gf; int n_obj; double* out; int* status;
+  __device__ long long total() const { return (long long)n_obj * 3 * PER_BAND; }
+  __device__ long long slot(long long fit) const {                      // column of this fit inside the 27-wide row
+    const int rem = (int)(fit / n_obj); const long long o = fit % n_obj;
+    const int j = rem / PER_BAND, q = (KIND == 0) ? rem % PER_BAND : (KIND == 1 ? 7 : 8);
+    return o * POWERLAW_COLS + 9 * j + q;
+  }
+  __device__ bool start(Job& job, long long fit) const {
+    const int rem = (int)(fit / n_obj); const long long o = fit % n_obj;
+    const int j = rem / PER_BAND, q = rem % PER_BAND;
+    const int band = (j == 0) ? BG : (j == 1 ? BR : BI);
+    const long long lo = seg_off[o * N_SEG + band];
+    const int n = (int)(seg_off[o * N_SEG + band + 1] - lo);
+    int code;
+    if (job.init(gt + lo, gf + lo, n, (KIND == 0) ? decline_index(q) : 0.0, code)) return true;
+    const long long s = slot(fit);
+    out[s] = qnan();
+    if (status) { status[s * 2] = code; status[s * 2 + 1] = 0; }
+    return false;
+  }
+  __device__ void done(const Job& job, long long fit, int rc) const {
+    const long long s = slot(fit);
+    out[s] = job.finish(rc);
+    if (status) { status[s * 2] = rc; status[s * 2 + 1] = job.trf.nfev; }
+  }
+};
+
+template <class P>
+__global__ void __launch_bounds__(FIT_THREADS, FIT_MIN_BLOCKS) k_fit_stage(P pol, StageIo io) {
+  using Job = typename P::Job;
+  using Carry = FitCarry<Job>;
+  const Carry* in = (const Carry*)io.in;
+  Carry* outc = (Carry*)io.out;
+  long long total;
+  int lanes = 32;                                     // lanes of a warp that take work
+  if (in) {
+    const unsigned c = *io.in_count;
+    total = c < io.in_capacity ? c : io.in_capacity;
+    const long long warps = (long long)gridDim.x * (FIT_THREADS / 32);
+    const long long per_warp = (total + warps - 1) / warps;      // fewer survivors than lanes: spread them over the warps
+    lanes = per_warp < 1 ? 1 : (per_warp > 32 ? 32 : (int)per_warp);
+  } else {
+    total = pol.total();
+  }
+  Job job;
+  bool active = false, exhausted = (int)(threadIdx.x & 31) >= lanes, may_export = outc != nullptr;
   long long fit = 0;
   for (;;) {
     for (int tries = 0; tries < 4 && !active && !exhausted; ++tries) {
-      fit = (long long)atomicAdd(ticket, 1ULL);
-      if (fit >= total) { exhausted = true; break; }
-      const int b = (int)(fit / n_obj); const long long o = fit % n_obj;    // band-major: lanes of a warp get bands of similar length
-      const long long lo = seg_off[o * N_SEG + b];
-      const int n = (int)(seg_off[o * N_SEG + b + 1] - lo);
-      int code;
-      active = job.init(gt + lo, gf + lo, ge + lo, n, code);
-      if (!active) {
-        job.finish(code, out + o * BAZIN_COLS + 8 * b);
-        if (status) { status[(o * N_BAND + b) * 2] = code; status[(o * N_BAND + b) * 2 + 1] = 0; }
-      }
+      const long long tk = (long long)atomicAdd(io.ticket, 1ULL);
+      if (tk >= total) { exhausted = true; break; }
+      if (in) { job = in[tk].job; fit = in[tk].fit; active = true; }
+      else { fit = tk; active = pol.start(job, fit); }
     }
-    if (!group_any(active || !exhausted)) break;      // also lines the warps up: they fetch the same code
+    if (!__syncthreads_or(active || !exhausted)) break;      // also lines the warps up: they fetch the same code
     if (active) {
       const int rc = job.step();
       if (rc != TRF_RUNNING) {
-        const int b = (int)(fit / n_obj); const long long o = fit % n_obj;
-        job.finish(rc, out + o * BAZIN_COLS + 8 * b);
-        if (status) { status[(o * N_BAND + b) * 2] = rc; status[(o * N_BAND + b) * 2 + 1] = job.trf.nfev; }
+        pol.done(job, fit, rc);
         active = false;
+      } else if (may_export && job.trf.nfev >= io.cap) {
+        const unsigned slot = atomicAdd(io.out_count, 1u);
+        if (slot < io.out_capacity) { outc[slot].job = job; outc[slot].fit = fit; active = false; }
+        else may_export = false;                      // carry buffer full: finish here
       }
     }
   }
@@ -79,86 +151,84 @@ __global__ void k_bazin_tail(int n_obj, double* __restrict__ out) {
   small_stats(chi, 6, c, m, sd); row[50] = c ? m : qnan(); row[51] = c ? sd : qnan();
 }
 
-// KIND 0: the seven fixed-index power laws (21 fits per object); 1: exponential; 2: linear (3 per object each)
-template <int KIND>
-__global__ void __launch_bounds__(FIT_THREADS, FIT_MIN_BLOCKS)
-k_decline_thread(const long long* __restrict__ seg_off, const double* __restrict__ gt, const double* __restrict__ gf,
-                 int n_obj, unsigned long long* __restrict__ ticket, double* __restrict__ out, int* __restrict__ status) {
-  constexpr int PER_BAND = (KIND == 0) ? 7 : 1;
-  const long long total = (long long)n_obj * 3 * PER_BAND;
-  DeclineJob<KIND> job;
-  bool active = false, exhausted = false;
-  long long fit = 0;
-  // (band, model)-major ticket order: the lanes of a warp fit the same model to the same band of different objects
-  auto slot = [&](long long ft) {                     // column of this fit inside the 27-wide row
-    const int rem = (int)(ft / n_obj); const long long o = ft % n_obj;
-    const int j = rem / PER_BAND, q = (KIND == 0) ? rem % PER_BAND : (KIND == 1 ? 7 : 8);
-    return o * POWERLAW_COLS + 9 * j + q;
-  };
-  for (;;) {
-    for (int tries = 0; tries < 4 && !active && !exhausted; ++tries) {
-      fit = (long long)atomicAdd(ticket, 1ULL);
-      if (fit >= total) { exhausted = true; break; }
-      const int rem = (int)(fit / n_obj); const long long o = fit % n_obj;
-      const int j = rem / PER_BAND, q = rem % PER_BAND;
-      const int band = (j == 0) ? BG : (j == 1 ? BR : BI);
-      const long long lo = seg_off[o * N_SEG + band];
-      const int n = (int)(seg_off[o * N_SEG + band + 1] - lo);
-      int code;
-      active = job.init(gt + lo, gf + lo, n, (KIND == 0) ? decline_index(q) : 0.0, code);
-      if (!active) {
-        const long long s = slot(fit);
-        out[s] = qnan();
-        if (status) { status[s * 2] = code; status[s * 2 + 1] = 0; }
-      }
+// Runs every fit of `pol` through the stages.  caps[0..n_caps) are the evaluation caps of the capped stages; one more,
+// uncapped stage follows.  carry_frac: size of the carry buffers as a fraction of the fits (a full buffer is not an error:
+// the fits that do not find room finish in the stage they are in).
+template <class P>
+int run_staged(const mlrn_store* s, const P& pol, long long fits, const int* caps, int n_caps, double carry_frac, cudaStream_t st) {
+  using Carry = FitCarry<typename P::Job>;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fit_stage<P>, FIT_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const long long full = (long long)s->sm_count * per_sm;
+  long long want = (fits + FIT_THREADS - 1) / FIT_THREADS;
+  const int grid0 = (int)(want < full ? (want > 0 ? want : 1) : full);
+  long long cap_l = (long long)(carry_frac * (double)fits);
+  if (cap_l < 8192) cap_l = 8192;
+  if (cap_l > fits) cap_l = fits;
+  const unsigned capacity = (unsigned)(cap_l < 0xffffffffLL ? cap_l : 0xffffffffLL);
+  unsigned long long* ctr = nullptr;                  // [MAX_STAGES] tickets, then [MAX_STAGES] carry counts (as unsigned)
+  Carry* buf[2] = {nullptr, nullptr};
+  MLRN_CUDA(cudaMallocAsync(&ctr, sizeof(unsigned long long) * 2 * MAX_STAGES, st));
+  cudaError_t e = cudaMemsetAsync(ctr, 0, sizeof(unsigned long long) * 2 * MAX_STAGES, st);
+  if (e == cudaSuccess && n_caps > 0) e = cudaMallocAsync(&buf[0], sizeof(Carry) * (size_t)capacity, st);
+  if (e == cudaSuccess && n_caps > 1) e = cudaMallocAsync(&buf[1], sizeof(Carry) * (size_t)capacity, st);
+  if (e == cudaSuccess) {
+    unsigned* counts = (unsigned*)(ctr + MAX_STAGES);
+    for (int stage = 0; stage <= n_caps; ++stage) {
+      StageIo io;
+      io.ticket = ctr + stage;
+      io.cap = stage < n_caps ? caps[stage] : INT_MAX;
+      io.in = stage > 0 ? buf[(stage - 1) & 1] : nullptr;
+      io.in_count = stage > 0 ? counts + 2 * (stage - 1) : nullptr;
+      io.in_capacity = capacity;
+      io.out = stage < n_caps ? buf[stage & 1] : nullptr;
+      io.out_count = stage < n_caps ? counts + 2 * stage : nullptr;
+      io.out_capacity = capacity;
+      // resumed stages: the survivor count is only known on the device, so they launch the full persistent grid and
+      // every warp reads it; a warp without work leaves at once
+      const long long cgrid = (long long)capacity / FIT_THREADS + 1;
+      const long long grid = stage == 0 ? grid0 : (cgrid < full ? cgrid : full);
+      k_fit_stage<P><<<(int)grid, FIT_THREADS, 0, st>>>(pol, io);
+      count_launch();
     }
-    if (!group_any(active || !exhausted)) break;
-    if (active) {
-      const int rc = job.step();
-      if (rc != TRF_RUNNING) {
-        const long long s = slot(fit);
-        out[s] = job.finish(rc);
-        if (status) { status[s * 2] = rc; status[s * 2 + 1] = job.trf.nfev; }
-        active = false;
-      }
-    }
+    e = cudaGetLastError();
   }
+  if (buf[0]) cudaFreeAsync(buf[0], st);
+  if (buf[1]) cudaFreeAsync(buf[1], st);
+  cudaFreeAsync(ctr, st);
+  if (e != cudaSuccess) return cuda_fail(e, "staged fit launch");
+  return MLRN_OK;
 }
 
-template <class K>
-int thread_fit_grid(K kernel, const mlrn_store* s, long long fits) {
-  int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, FIT_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
-  long long want = (fits + FIT_THREADS - 1) / FIT_THREADS;
-  long long cap = (long long)s->sm_count * per_sm;
-  return (int)(want < cap ? (want > 0 ? want : 1) : cap);
-}
+#ifndef FIT_STAGE_CAPS
+#define FIT_STAGE_CAPS {128, 256, 512, 1024}
+#endif
+#ifndef FIT_DECLINE_CAPS
+#define FIT_DECLINE_CAPS {64, 256}
+#endif
 
 }  // namespace
 
 int run_bazin(const mlrn_store* s, double* out_dev, int* status_dev, cudaStream_t st) {
   if (s->n_obj == 0) return MLRN_OK;
-  MLRN_CUDA(cudaMemsetAsync(s->ticket, 0, sizeof(unsigned long long), st));
-  const int grid = thread_fit_grid(k_bazin_thread, s, (long long)s->n_obj * N_BAND);
-  k_bazin_thread<<<grid, FIT_THREADS, 0, st>>>(s->seg_off, s->t, s->flux, s->err, s->n_obj, s->ticket, out_dev, status_dev);
+  const int caps[] = FIT_STAGE_CAPS;
+  BazinPolicy pol{s->seg_off, s->t, s->flux, s->err, s->n_obj, out_dev, status_dev};
+  const int rc = run_staged(s, pol, (long long)s->n_obj * N_BAND, caps, (int)(sizeof(caps) / sizeof(int)), 0.15, st);
+  if (rc != MLRN_OK) return rc;
   k_bazin_tail<<<(s->n_obj + 255) / 256, 256, 0, st>>>(s->n_obj, out_dev);
   MLRN_CUDA(cudaGetLastError());
-  count_launch(2);
+  count_launch();
   return MLRN_OK;
 }
 
 int run_powerlaw(const mlrn_store* s, double* out_dev, int* status_dev, cudaStream_t st) {
   if (s->n_obj == 0) return MLRN_OK;
-  MLRN_CUDA(cudaMemsetAsync(s->ticket + 4, 0, 3 * sizeof(unsigned long long), st));
-  k_decline_thread<0><<<thread_fit_grid(k_decline_thread<0>, s, (long long)s->n_obj * 21), FIT_THREADS, 0, st>>>(
-      s->seg_off, s->t, s->flux, s->n_obj, s->ticket + 4, out_dev, status_dev);
-  k_decline_thread<1><<<thread_fit_grid(k_decline_thread<1>, s, (long long)s->n_obj * 3), FIT_THREADS, 0, st>>>(
-      s->seg_off, s->t, s->flux, s->n_obj, s->ticket + 5, out_dev, status_dev);
-  k_decline_thread<2><<<thread_fit_grid(k_decline_thread<2>, s, (long long)s->n_obj * 3), FIT_THREADS, 0, st>>>(
-      s->seg_off, s->t, s->flux, s->n_obj, s->ticket + 6, out_dev, status_dev);
-  MLRN_CUDA(cudaGetLastError());
-  count_launch(3);
-  return MLRN_OK;
+  const int caps[] = FIT_DECLINE_CAPS;
+  const int n_caps = (int)(sizeof(caps) / sizeof(int));
+  int rc = run_staged(s, DeclinePolicy<0>{s->seg_off, s->t, s->flux, s->n_obj, out_dev, status_dev}, (long long)s->n_obj * 21, caps, n_caps, 0.10, st);
+  if (rc == MLRN_OK) rc = run_staged(s, DeclinePolicy<1>{s->seg_off, s->t, s->flux, s->n_obj, out_dev, status_dev}, (long long)s->n_obj * 3, caps, n_caps, 0.10, st);
+  if (rc == MLRN_OK) rc = run_staged(s, DeclinePolicy<2>{s->seg_off, s->t, s->flux, s->n_obj, out_dev, status_dev}, (long long)s->n_obj * 3, caps, n_caps, 0.10, st);
+  return rc;
 }
 
 }  // namespace mlrn
