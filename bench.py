@@ -1,30 +1,27 @@
 #!/usr/bin/env python
 """bench.py -- objects/s of the MALLORN light-curve featurisation on B200 (contract in the task statement).
 
-A *step* is one pass of the hot path over one batch of synthetic light curves: K1 pack (flat
-long-format rows -> CSR (object, band) segments in HBM) followed by every feature pass the
-library exports (statistical, colors, shape, tde_physics, physics_based, bazin, power-law,
-2-D GP), i.e. the full 434-column module table the v34a/v92d 222-feature set is selected from.
+A *step* is one pass of the hot path over one batch of synthetic light curves: K1 pack (flat long-format rows -> CSR
+(object, band) segments in HBM) followed by every feature pass of the 434-column module table the v34a/v92d 222-feature set
+is selected from (statistical, colors, shape, tde_physics, physics_based, bazin, power-law, 2-D GP), through the product's
+own entry points (``shard.featurise_shard`` / ``shard.featurise_sharded``).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--objects M] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c4|c5|c1|c2|c3]
 
-* ``value``  objects/s, inputs resident in HBM (flat columns on the device) when the clock starts.
-* ``e2e``    the same through the C-ABI with HOST buffers: H2D of the five input columns and D2H of
-             every feature table inside the timed region.
-* ``roofline`` the moment pass (north star: judged against HBM bandwidth), CUDA-event timed inside
-             the step; ``passes`` lists every pass's share of the step.
-* ``cpu_baseline`` the CPU oracle (``oracle/``: the reference's numpy/scipy arithmetic) on a bounded
-             sample of the same workload, all host cores.
-* ``widened``  SURVEY 8(f) rows built so far, measured beside the step and not part of ``value`` (the 434-column
-             table): the per-band 1-D GP pass (``extract_gp_features``, 21 columns) on a slice of the same batch, and
-             the native CSV ingest against the reference's pandas loading path on the box's host cores, and the
-             DataFrame-in / DataFrame-out call (``extract_feature_tables``) on the 10,178-object C1-shaped set.
-* ``--impl reference`` times only that CPU path (the reference has no GPU path and, being a Python
-             package with no native code, "the reference's own CPU implementation" is the oracle
-             restatement: ``/root/reference`` does not exist on the GPU box).
-
-N > 1: launched by torchrun, one rank per GPU; objects are sharded (weak scaling, fixed objects per
-GPU), no collective during compute, one NCCL all-gather of the feature table at the end of each step.
+* N = 1 (default ``--config c4``): BASELINE.json configs[3], 10^6 objects on one B200.
+* N > 1 (default ``--config c5``, launched by torchrun): BASELINE.json configs[4], ONE fixed 10^7-object set, each rank
+  generates and featurises its contiguous range (strong scaling), no collective during compute, ONE NCCL all-gather of
+  the concatenated float64 table at the end of each step.
+* ``--config c1|c2|c3``: the 10,178-object configs through the DataFrame-in / DataFrame-out API with the host / device
+  split (c1 statistics + Bazin, c2 the 2-D GP, c3 power law + the full table).
+* ``value``  objects/s, inputs resident in HBM when the clock starts; ``e2e`` the same through the C-ABI with HOST buffers
+  (H2D of the input columns and D2H of this rank's feature table inside the timed region).
+* ``roofline`` the moment pass against measured HBM bandwidth; ``roofline_dominant`` the GP pass against the FP64 rate
+  measured on the device in this run (``mlrn_measure_fp64``); ``passes`` every pass's share of the step.
+* ``cpu_baseline`` the CPU oracle (``oracle/``: the reference's numpy/scipy arithmetic) on a bounded sample, all host cores.
+* ``--impl reference`` times only that CPU path (the reference is a Python package without native code and
+  ``/root/reference`` does not exist on the GPU box, so "the reference's own CPU implementation" is the oracle port); its
+  ``config.workload`` names the sample it actually timed.
 """
 from __future__ import annotations
 
@@ -46,10 +43,14 @@ MODULE_WIDTH = {"statistical": 123, "colors": 83, "shape": 65, "tde": 25, "physi
 MODULES = ("statistical", "colors", "shape", "tde", "physics", "bazin", "powerlaw", "gp2d")
 METRIC = "light curves/sec for the 222-feature set (full 434-column module table)"
 UNIT = "objects/s"
-SEED = 20260118 + 3            # seed = 20260118 + config index (C4)
-# DRAM traffic of the moment pass from `ncu --set full` (profiles/r01_stat_v2_full.txt: 793.78 MB read + 184.05 MB
-# written for 200,000 objects of this generator) -- 0.99x the algorithmic bytes, i.e. no re-reads
-NCU_STAT_DRAM_BYTES_PER_OBJECT = (793.778688e6 + 184.050432e6) / 200_000
+BASE_SEED = 20260118           # seed = 20260118 + config index
+C5_OBJECTS = 10_000_000
+# ncu --set full captures of THIS build's kernels (profiles/r02_*.txt), per object; see profiles/README.md
+NCU = {"stat_dram_bytes_per_object": None, "stat_source": None, "fits": None}
+try:
+    NCU.update(json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_constants.json"))))
+except Exception:
+    pass
 
 
 # ----------------------------------------------------------------------------------------------
@@ -109,39 +110,53 @@ def _cpu_chunk(args):
     cols, lo, hi, modules = args
     keep = (cols["obj"] >= lo) & (cols["obj"] < hi)
     obj = (cols["obj"][keep] - lo).astype(np.int32)
+    out = {}
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         for m in modules:
-            run_module(m, obj, cols["band"][keep], cols["t"][keep], cols["flux"][keep], cols["err"][keep],
-                       hi - lo, cols["z"][lo:hi])
-    return hi - lo
+            out[m] = run_module(m, obj, cols["band"][keep], cols["t"][keep], cols["flux"][keep], cols["err"][keep],
+                                hi - lo, cols["z"][lo:hi])
+    return lo, hi, out
 
 
-def cpu_rate(cols, n_objects, modules, cores):
-    """objects/s of the CPU oracle on the first ``n_objects`` objects, ``cores`` worker processes."""
+def cpu_run(cols, n_objects, modules, cores, keep_rows=False):
+    """The CPU oracle on the first ``n_objects`` objects, ``cores`` worker processes.  Returns (objects/s, seconds, rows)
+    with rows = {module: [n_objects, cols]} when ``keep_rows``."""
     import multiprocessing as mp
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     per = max(1, (n_objects + cores * 2 - 1) // (cores * 2))
     jobs = [(cols, lo, min(lo + per, n_objects), modules) for lo in range(0, n_objects, per)]
     t0 = time.perf_counter()
     if cores == 1:
-        done = sum(_cpu_chunk(j) for j in jobs)
+        parts = [_cpu_chunk(j) for j in jobs]
     else:
         with mp.get_context("fork").Pool(cores) as pool:
-            done = sum(pool.map(_cpu_chunk, jobs))
+            parts = pool.map(_cpu_chunk, jobs)
     dt = time.perf_counter() - t0
-    return done / dt, dt
+    rows = None
+    if keep_rows:
+        rows = {m: np.full((n_objects, MODULE_WIDTH[m]), np.nan) for m in modules}
+        for lo, hi, out in parts:
+            for m, (present, r) in out.items():
+                rows[m][lo + present] = r
+    return n_objects / dt, dt, rows
 
 
-def host_sample(n_objects):
+def cpu_rate(cols, n_objects, modules, cores):
+    rate, dt, _ = cpu_run(cols, n_objects, modules, cores)
+    return rate, dt
+
+
+def host_sample(n_objects, config_index=3):
     from mallorn_astrophysics_b200.synth import make_table
-    tb = make_table(n_objects, seed=SEED)
+    tb = make_table(n_objects, seed=BASE_SEED + config_index)
     return {"obj": tb.obj, "band": tb.band, "t": tb.t, "flux": tb.flux, "err": tb.err, "z": tb.z}
 
 
-def ingest_rates(n_objects=2000):
-    """SURVEY 8(f) row 1 measured on this box's host cores: the reference's loading path (pd.read_csv of the split
-    files + concat, then the factorisation) against the native ingest (libmallorn_ingest.so) on the same files."""
+def ingest_rates(n_objects=2000, device=0):
+    """SURVEY 8(f) row 1 measured on this box: the reference's loading path (pd.read_csv of the split files + concat, then
+    the factorisation) against the native ingest (libmallorn_ingest.so) on the same files, and files -> feature table
+    through the chunked, overlapped pipeline."""
     import shutil
     import tempfile
     import pandas as pd
@@ -150,7 +165,7 @@ def ingest_rates(n_objects=2000):
     from mallorn_astrophysics_b200.synth import make_table
     root = tempfile.mkdtemp(prefix="mlrn_bench_ingest_")
     try:
-        lc = make_table(n_objects, seed=SEED).to_frame()
+        lc = make_table(n_objects, seed=BASE_SEED + 3).to_frame()
         edges = np.linspace(0, len(lc), 5).astype(int)
         paths = []
         for i in range(4):
@@ -169,34 +184,67 @@ def ingest_rates(n_objects=2000):
         same = bool(np.array_equal(got.obj, ref[0]) and np.array_equal(got.band, ref[1]) and
                     all(np.array_equal(a.view(np.uint64), b.view(np.uint64))
                         for a, b in ((got.t, ref[2]), (got.flux, ref[3]), (got.err, ref[4]))))
-        return {"reference": "load_lightcurves (data_loader.py:36-62) + groupby factorisation", "rows": int(len(lc)),
-                "csv_bytes": int(size), "pandas_mb_per_s": size / 1e6 / t_ref, "native_mb_per_s": size / 1e6 / t_nat,
-                "native_rows_per_s": len(lc) / t_nat, "threads": os.cpu_count(), "bit_identical_to_pandas": same}
+        out = {"reference": "load_lightcurves (data_loader.py:36-62) + groupby factorisation", "rows": int(len(lc)),
+               "csv_bytes": int(size), "pandas_mb_per_s": size / 1e6 / t_ref, "native_mb_per_s": size / 1e6 / t_nat,
+               "native_rows_per_s": len(lc) / t_nat, "threads": os.cpu_count(), "bit_identical_to_pandas": same}
+        if hasattr(ingest, "featurise_files"):
+            try:
+                ingest.featurise_files(paths, ("statistical", "colors", "shape", "tde"), device=device)       # warm
+                t0 = time.perf_counter()
+                _, _, info = ingest.featurise_files(paths, ("statistical", "colors", "shape", "tde"), device=device)
+                out["files_to_table_seconds"] = time.perf_counter() - t0
+                out["files_to_table"] = info
+            except Exception as exc:
+                out["files_to_table_error"] = f"{type(exc).__name__}: {exc}"
+        return out
     except Exception as exc:                                                # never lose the bench line over the side measurement
         return {"error": f"{type(exc).__name__}: {exc}"}
     finally:
         shutil.rmtree(root, ignore_errors=True)
 
 
-def frames_e2e(n_objects=10178, device=0):
-    """The user-facing call itself on the C1-sized set (BASELINE.json configs[0] shape): the reference's long DataFrame in,
-    the reference's per-module DataFrames out (features.pipeline.extract_feature_tables = one K1 pack, the eight passes of
-    the 434-column table), host factorisation and DataFrame assembly included."""
+def frames_e2e(n_objects=10178, device=0, modules=MODULES, config_index=1):
+    """The user-facing call itself on a 10,178-object set (BASELINE.json configs[0..2] shape): the reference's long
+    DataFrame in, the reference's per-module DataFrames out (features.pipeline.extract_feature_tables = one K1 pack + the
+    passes), host factorisation and DataFrame assembly included, with the host / device split."""
     try:
+        import torch
         from mallorn_astrophysics_b200.features.pipeline import extract_feature_tables
+        from mallorn_astrophysics_b200.store import LightCurveStore, frame_columns
         from mallorn_astrophysics_b200.synth import make_table
-        tb = make_table(n_objects, config_index=1)
+        tb = make_table(n_objects, config_index=config_index)
         lc, meta, ids = tb.to_frame(), tb.metadata_frame(), list(tb.object_ids)
         warm = ids[:512]
-        extract_feature_tables(lc[lc["object_id"].isin(set(warm))], meta, warm, modules=MODULES, device=device)
+        extract_feature_tables(lc[lc["object_id"].isin(set(warm))], meta, warm, modules=modules, device=device)
         t0 = time.perf_counter()
-        tables = extract_feature_tables(lc, meta, ids, modules=MODULES, device=device)
+        tables = extract_feature_tables(lc, meta, ids, modules=modules, device=device)
         dt = time.perf_counter() - t0
+        # the split: host factorisation alone, and the device part alone (pack + passes with host buffers, no frames)
+        t0 = time.perf_counter()
+        codes, band, t, flux, err, _ = frame_columns(lc, ids)
+        t_fact = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        with LightCurveStore(codes, band, t, flux, err, len(ids), device=device) as s:
+            for m in modules:
+                s.features(m, z=tb.z if m == "physics" else None)
+        torch.cuda.synchronize(device)
+        t_dev = time.perf_counter() - t0
         return {"call": "features.pipeline.extract_feature_tables(lightcurves, metadata, object_ids)", "objects": int(n_objects),
                 "rows": int(len(lc)), "seconds": dt, "objects_per_s": n_objects / dt,
-                "columns": int(sum(len(t.columns) - 1 for t in tables.values()))}
+                "host_factorise_seconds": t_fact, "device_pack_and_passes_seconds": t_dev,
+                "frame_assembly_seconds": max(dt - t_fact - t_dev, 0.0),
+                "columns": int(sum(len(t.columns) - 1 for t in tables.values())), "modules": list(modules)}
     except Exception as exc:                                                # never lose the bench line over the side measurement
         return {"error": f"{type(exc).__name__}: {exc}"}
+
+
+def reference_workload(per_step, modules, n_rows):
+    return {"workload": f"CPU reference arm: {per_step} objects per step of the C4 generator (seed {BASE_SEED + 3}, {n_rows} "
+                        f"observations) -- a bounded SAMPLE of BASELINE.json configs[3], not the 10^6-object set; objects/s "
+                        f"extrapolates linearly (objects are independent)",
+            "sample_objects_per_step": per_step, "same_config_as_gpu_arm": False, "bands": 6, "mean_obs_per_object": 150,
+            "modules": list(modules), "columns": sum(MODULE_WIDTH[m] for m in modules),
+            "parallelism": "one process per host core over object chunks (the reference itself is single-process)"}
 
 
 def run_reference_arm(args):
@@ -214,27 +262,32 @@ def run_reference_arm(args):
         cpu_rate(cols, per_step, modules, cores)
     dt = time.perf_counter() - t0
     value = per_step * args.steps / dt
-    sample = f"{per_step} objects/step of the C4 generator (seed {SEED}), {len(cols['obj'])} observations"
+    sample = f"{per_step} objects/step of the C4 generator (seed {BASE_SEED + 3}), {len(cols['obj'])} observations, {cores} host cores"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": dict(workload_config(args, args.objects, modules), sample_objects_per_step=per_step),
+        "config": reference_workload(per_step, modules, int(len(cols["obj"]))),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "host_cores": cores,
     }))
 
 
-def workload_config(args, objects_per_gpu, modules):
-    return {"workload": "C4: 1M-object LSST-like synthetic set, full feature table (BASELINE.json configs[3])"
-            if objects_per_gpu == 1_000_000 else
-            f"C4 generator at {objects_per_gpu} objects per GPU (BASELINE.json configs[3] shape)",
-            "objects_per_gpu": objects_per_gpu, "bands": 6, "mean_obs_per_object": 150,
+def workload_config(name, world, n_total, n_local, modules, n_rows):
+    if name == "c5":
+        label = (f"C5: one fixed {n_total}-object LSST-scale synthetic set sharded over {world} B200 (BASELINE.json configs[4]); "
+                 f"each rank generates and featurises its contiguous range, one all-gather of the float64 table")
+    elif n_total == 1_000_000:
+        label = "C4: 1M-object LSST-like synthetic set, full feature table (BASELINE.json configs[3])"
+    else:
+        label = f"C4 generator at {n_total} objects (BASELINE.json configs[3] shape)"
+    return {"workload": label, "objects_total": n_total, "objects_this_rank": n_local, "bands": 6, "mean_obs_per_object": 150,
             "modules": list(modules), "columns": sum(MODULE_WIDTH[m] for m in modules),
-            "l2": "inputs larger than L2 (no flush needed)" if objects_per_gpu * 150 * 25 > 2 * 126e6 else
-                  "L2 flushed between steps",
-            "parallelism": f"objects sharded over {args.gpus} GPU(s), all-gather of the feature table"}
+            "l2": "inputs larger than L2 (no flush needed)" if n_rows * 25 > 2 * 126e6 else "L2 flushed between steps",
+            "parallelism": f"objects sharded over {world} GPU(s) (shard.featurise_sharded), one NCCL all-gather of the "
+                           f"[objects, {sum(MODULE_WIDTH[m] for m in modules)}] float64 table" if world > 1 else
+                           "one GPU (shard.featurise_shard)"}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -250,9 +303,8 @@ def algorithmic_bytes(n_rows, n_obj):
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
-    from mallorn_astrophysics_b200 import _native
-    from mallorn_astrophysics_b200.store import LightCurveStore
-    from mallorn_astrophysics_b200.synth import make_columns_device
+    from mallorn_astrophysics_b200 import _native, shard
+    from mallorn_astrophysics_b200.synth import make_shard_columns_device
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -266,17 +318,26 @@ def run_gpu_arm(args):
               "physics": "mlrn_physics", "bazin": "mlrn_bazin", "powerlaw": "mlrn_powerlaw", "gp2d": "mlrn_gp2d",
               "gp1d": "mlrn_gp1d"}
     modules = [m for m in (args.modules.split(",") if args.modules else MODULES) if hasattr(L, symbol[m])]
-    n_obj = args.objects
-    cols = make_columns_device(n_obj, SEED * 131 + rank, dev)
+    config = args.config or ("c5" if world > 1 else "c4")
+    if config == "c5":
+        n_total = args.objects or C5_OBJECTS
+        seed = (BASE_SEED + 4) * 131
+    else:
+        n_total = (args.objects or 1_000_000) * world
+        seed = (BASE_SEED + 3) * 131
+    ranges = shard.equal_ranges(n_total, world)
+    lo, hi = ranges[rank]
+    n_obj = hi - lo
+    cols = make_shard_columns_device(n_total, lo, hi, seed, dev)            # this rank's objects of the ONE set, in HBM
     n_rows = int(cols["obj"].shape[0])
     stream = torch.cuda.current_stream()
     sptr = stream.cuda_stream
-    outs = {m: torch.empty((n_obj, _native.COLS[m]), dtype=torch.float64, device=dev) for m in modules}
-    width = sum(_native.COLS[m] for m in modules)
+    width = shard.table_width(modules)
     table = torch.empty((n_obj, width), dtype=torch.float64, device=dev)
-    gathered = torch.empty((world * n_obj, width), dtype=torch.float64, device=dev) if world > 1 else None
+    rows_per_rank = [b - a for a, b in ranges]
+    gathered = torch.empty((world * max(rows_per_rank), width), dtype=torch.float64, device=dev) if world > 1 else None
     gp_status = torch.zeros((n_obj, 4), dtype=torch.int32, device=dev) if "gp2d" in modules else None
-    gp1_status = torch.zeros((n_obj, 12), dtype=torch.int32, device=dev) if "gp1d" in modules else None
+    status = {"gp2d": gp_status} if gp_status is not None else {}
     flush = None
     if n_rows * 25 < 2 * 126e6:
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -289,22 +350,15 @@ def run_gpu_arm(args):
     def step(timed: bool):
         marks = [("start", ev())]
         marks[0][1].record(stream)
-        store = LightCurveStore(cols["obj"], cols["band"], cols["t"], cols["flux"], cols["err"], n_obj,
-                                device=local, stream=sptr)
-        e = ev(); e.record(stream); marks.append(("pack", e))
-        c0 = 0
-        for m in modules:
-            store.features(m, z=cols["z"] if m == "physics" else None, out=outs[m],
-                           status=gp_status if m == "gp2d" else (gp1_status if m == "gp1d" else None))
-            w = _native.COLS[m]
-            table[:, c0:c0 + w].copy_(outs[m])
-            c0 += w
-            e = ev(); e.record(stream); marks.append((m, e))
+
+        def mark(name):
+            e = ev(); e.record(stream); marks.append((name, e))
+
+        shard.featurise_shard(cols, n_obj, modules, table=table, device=local, stream=sptr, status=status, on_pass=mark)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, table)
-            e = ev(); e.record(stream); marks.append(("allgather", e))
+            shard.allgather_table(table, rows_per_rank, out=gathered)
+            mark("allgather")
         stream.synchronize()
-        store.close()
         if timed:
             for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
                 pass_ms[name] += a.elapsed_time(b)
@@ -333,40 +387,13 @@ def run_gpu_arm(args):
         tms = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms = float(tms.item())
-    value = world * n_obj * args.steps / (ms * 1e-3)
-
-    # ---- end to end: host buffers through the C-ABI, copies inside the timed region
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    host = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v) for k, v in cols.items()}
-    hnp = {k: v.numpy() for k, v in host.items()}
-    houts = {m: torch.empty((n_obj, _native.COLS[m]), dtype=torch.float64, pin_memory=True).numpy() for m in modules}
-    h2d = sum(hnp[k].nbytes for k in ("obj", "band", "t", "flux", "err")) + (hnp["z"].nbytes if "physics" in modules else 0)
-    d2h = sum(a.nbytes for a in houts.values())
-
-    def e2e_step():
-        store = LightCurveStore(hnp["obj"], hnp["band"], hnp["t"], hnp["flux"], hnp["err"], n_obj,
-                                device=local, stream=sptr)
-        for m in modules:
-            store.features(m, z=hnp["z"] if m == "physics" else None, out=houts[m])
-        store.close()
-
-    for _ in range(min(args.warmup, 3)):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        tms = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        e2e_s = float(tms.item())
-    e2e_value = world * n_obj * e2e_steps / e2e_s
+    value = n_total * args.steps / (ms * 1e-3)
+    step_s = ms * 1e-3 / args.steps
 
     # ---- section 8(f) row measured beside the step: the per-band 1-D GP pass (extract_gp_features), on a bounded slice
     widened = None
-    if hasattr(L, "mlrn_gp1d") and "gp1d" not in modules and not args.modules and args.gp1d_objects > 0:
+    if rank == 0 and hasattr(L, "mlrn_gp1d") and "gp1d" not in modules and not args.modules and args.gp1d_objects > 0:
+        from mallorn_astrophysics_b200.store import LightCurveStore
         k = min(n_obj, args.gp1d_objects)
         keep = cols["obj"] < k
         sub = {c: cols[c][keep].contiguous() for c in ("obj", "band", "t", "flux", "err")}
@@ -389,7 +416,43 @@ def run_gpu_arm(args):
                             "observations": int(sub["obj"].shape[0]), "launches": 1}}
         del sub, o1, s1
 
+    # ---- end to end: host buffers through the C-ABI, copies inside the timed region
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    e2e_warm = min(args.warmup, 3)
+    if step_s > 8.0:                                   # long steps (big shards): one warm-up and one timed step bound the run
+        e2e_steps, e2e_warm = 1, 1
+    host = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v) for k, v in cols.items()}
+    hnp = {k: v.numpy() for k, v in host.items()}
+    torch.cuda.synchronize()
+    cols = None                                        # the device-resident inputs are not needed any more (big shards: 20+ GB)
+    htable = torch.empty((n_obj, width), dtype=torch.float64, pin_memory=True)
+    h2d = sum(hnp[k].nbytes for k in ("obj", "band", "t", "flux", "err")) + (hnp["z"].nbytes if "physics" in modules else 0)
+    d2h = htable.numel() * 8
+
+    def e2e_step():
+        shard.featurise_shard(hnp, n_obj, modules, table=table, device=local, stream=sptr)
+        if world > 1:
+            shard.allgather_table(table, rows_per_rank, out=gathered)
+        htable.copy_(table, non_blocking=True)
+        stream.synchronize()
+
+    for _ in range(e2e_warm):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tms = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        e2e_s = float(tms.item())
+    e2e_value = n_total * e2e_steps / e2e_s
+    del host, hnp, htable
+
     if rank == 0:
+        import ctypes
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -400,26 +463,31 @@ def run_gpu_arm(args):
         roof = None
         if stat_ms:
             ach = algorithmic_bytes(n_rows, n_obj) / (stat_ms * 1e-3) / 1e9
+            per_obj = NCU.get("stat_dram_bytes_per_object")
             roof = {"kernel": "k_stat (moment pass, stat_fast.cu)", "bound": "hbm", "achieved": ach, "peak": peak,
                     "unit": "GB/s", "frac": ach / peak,
-                    "traffic": NCU_STAT_DRAM_BYTES_PER_OBJECT * n_obj,
-                    "traffic_source": "ncu --set full capture at 200k objects (profiles/r01_stat_v2_full.txt), scaled per object",
+                    "traffic": per_obj * n_obj if per_obj else None,
+                    "traffic_source": NCU.get("stat_source"),
                     "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s",
                     "algorithmic_bytes_per_launch": algorithmic_bytes(n_rows, n_obj), "ms_per_launch": stat_ms}
         roof_gp = None
         if gp_status is not None and pass_ms.get("gp2d"):
             # dominant kernel of the step: FP64 work of the GP = (evaluations + the one at the optimum) x N^3 flop
-            # (N^3/2 FMA per -lnL + gradient evaluation) over its CUDA-event time
+            # (N^3/2 FMA per -lnL + gradient evaluation) over its CUDA-event time, against the FP64
+            # rate measured on this device right now (the DMMA loop: the instruction the sweep issues)
+            dfma, dmma = ctypes.c_double(0.0), ctypes.c_double(0.0)
+            rc = L.mlrn_measure_fp64(local, ctypes.byref(dfma), ctypes.byref(dmma))
+            fp64_peak = max(dfma.value, dmma.value) if rc == 0 and max(dfma.value, dmma.value) > 0 else 37.1
             stt = gp_status.to(torch.float64)
             fitted = stt[:, 3] >= 10
             flop = float((((stt[:, 1] + 1.0) * stt[:, 3] ** 3)[fitted]).sum())
             gp_ms = pass_ms["gp2d"] / args.steps
             ach_tf = flop / (gp_ms * 1e-3) / 1e12
-            roof_gp = {"kernel": "k_gp2d (2-D GP, 61 % of the step)", "bound": "tensor", "achieved": ach_tf, "peak": 37.1,
-                       "unit": "TFLOP/s", "frac": ach_tf / 37.1, "traffic": None,
-                       "peak_source": "FP64 DMMA/DFMA rate measured on this pool's B200 with tests/micro/fp64_rates.cu "
-                                      "(64 FMA/clk/SM); MEASURED_PEAKS.json has no FP64 figure",
-                       "algorithmic_flop_per_launch": flop, "ms_per_launch": gp_ms,
+            roof_gp = {"kernel": "k_gp2d (2-D GP)", "bound": "tensor", "achieved": ach_tf, "peak": fp64_peak,
+                       "unit": "TFLOP/s", "frac": ach_tf / fp64_peak, "traffic": None,
+                       "peak_source": f"measured in this run on cuda:{local} (mlrn_measure_fp64: DFMA {dfma.value:.2f}, "
+                                      f"DMMA m8n8k4 {dmma.value:.2f} TFLOP/s)" if rc == 0 else "fallback 37.1 TFLOP/s (round-1 measurement)",
+                       "algorithmic_flop_per_launch": flop, "ms_per_launch": gp_ms, "share_of_step": pass_ms["gp2d"] / ms,
                        "mean_evaluations": float(stt[:, 1][fitted].mean()), "mean_points": float(stt[:, 3][fitted].mean())}
         cpu = None
         if not args.no_cpu:
@@ -428,32 +496,94 @@ def run_gpu_arm(args):
             sample_cols = host_sample(n_cpu)
             rate, secs = cpu_rate(sample_cols, n_cpu, modules, cores)
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{n_cpu} objects of the same generator (seed {SEED}), modules {','.join(modules)}, "
+                   "sample": f"{n_cpu} objects of the C4 generator (seed {BASE_SEED + 3}), modules {','.join(modules)}, "
                              f"{secs:.1f} s on {cores} processes"}
             if widened is not None:
                 n_w = min(n_cpu, 8 * cores)
                 rate_w, secs_w = cpu_rate(sample_cols, n_w, ["gp1d"], cores)
                 widened["gp1d"]["cpu_baseline"] = {"value": rate_w, "unit": UNIT, "cores": cores, "kind": "port",
                                                    "sample": f"first {n_w} objects of the CPU sample, oracle/gp1d.py, {secs_w:.1f} s"}
-                widened["ingest"] = ingest_rates()
+                widened["ingest"] = ingest_rates(device=local)
                 widened["frames_e2e"] = frames_e2e(device=local)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if config == "c5" else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, n_obj, modules),
+            "config": workload_config(config, world, n_total, n_obj, modules, n_rows),
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps},
+                    "steps": e2e_steps, "call": "shard.featurise_shard(host columns) + all-gather + D2H of this rank's table"},
             "gpu_launches": int(launches),
-            "roofline": roof, "roofline_dominant": roof_gp, "cpu_baseline": cpu,
+            "roofline": roof, "roofline_dominant": roof_gp, "roofline_fits": NCU.get("fits"), "cpu_baseline": cpu,
             "passes": {k: {"ms_per_step": v / args.steps, "share": v / ms} for k, v in pass_ms.items() if v > 0},
-            "observations_per_gpu": n_rows,
+            "observations_this_rank": n_rows,
             "widened": widened,
         }
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------
+# the 10,178-object configs (BASELINE.json configs[0..2]) through the DataFrame API
+# ----------------------------------------------------------------------------------------------
+def run_small_config(args):
+    """One JSON line for c1 / c2 / c3: the reference-facing call (DataFrames in and out) on the 10,178-object set, its
+    host / device split, the CPU oracle on the same objects and -- for the fit passes -- the parity classes on the set."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import warnings
+    import torch
+    from mallorn_astrophysics_b200.synth import make_table
+    name = args.config
+    modules = {"c1": ("statistical", "colors", "shape", "physics", "bazin"), "c2": ("gp2d",),
+               "c3": MODULES}[name]
+    ci = {"c1": 0, "c2": 1, "c3": 2}[name]
+    label = {"c1": "C1: v34a base statistics + Bazin fits on the 10,178-object set (BASELINE.json configs[0])",
+             "c2": "C2: v19 2-D multi-band GP features on the 10,178-object set (BASELINE.json configs[1])",
+             "c3": "C3: v55 power law + the full v92d module table on the 10,178-object set (BASELINE.json configs[2])"}[name]
+    n = args.objects or 10178
+    cores = os.cpu_count() or 1
+    tb = make_table(n, config_index=ci)
+    cols = {"obj": tb.obj, "band": tb.band, "t": tb.t, "flux": tb.flux, "err": tb.err, "z": tb.z}
+    n_cpu = n if args.full_cpu else min(n, args.cpu_objects or 64 * cores)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        rate, secs, cpu_rows = cpu_run(cols, n_cpu, list(modules), cores, keep_rows=True)      # forks before CUDA is touched
+    torch.cuda.set_device(0)
+    runs = [frames_e2e(n, 0, modules, ci) for _ in range(max(1, args.steps))]
+    best = min(runs, key=lambda r: r.get("seconds", 1e30))
+    parity = {}
+    if "error" not in best:
+        from fitparity import classify_bazin, classify_r2
+        from mallorn_astrophysics_b200.store import LightCurveStore
+        with LightCurveStore.from_table(tb.subset(n_cpu)) as s:
+            got = {m: s.features(m, z=tb.z[:n_cpu] if m == "physics" else None) for m in modules}
+        for m in modules:
+            g, w = got[m], cpu_rows[m]
+            if m == "bazin":
+                parity[m] = classify_bazin(g, w)
+            elif m == "powerlaw":
+                parity[m] = classify_r2(g, w)
+            else:
+                ok = ~np.isnan(w) & ~np.isnan(g)
+                rel = np.abs(g[ok] - w[ok]) / np.maximum(np.abs(w[ok]), 1e-9)
+                tol = 1e-3 if m == "gp2d" else 1e-5
+                parity[m] = {"cells": int(w.size), "nan_pattern_mismatch": int((np.isnan(g) != np.isnan(w)).sum()),
+                             "beyond_tolerance": int((rel > tol).sum()), "tolerance": tol}
+    print(json.dumps({
+        "metric": METRIC, "value": best.get("objects_per_s"), "unit": UNIT, "n_gpus": 1, "steps": len(runs), "warmup": 1,
+        "ms_per_step": 1e3 * best.get("seconds", float("nan")), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": label, "objects": n, "modules": list(modules), "columns": sum(MODULE_WIDTH[m] for m in modules),
+                   "api": "features.pipeline.extract_feature_tables (DataFrames in, DataFrames out)"},
+        "e2e": {"value": best.get("objects_per_s"), "unit": UNIT, "h2d_bytes_per_step": int(29 * tb.n_rows),
+                "d2h_bytes_per_step": int(8 * n * sum(MODULE_WIDTH[m] for m in modules))},
+        "frames": best,
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"first {n_cpu} objects of the same set, modules {','.join(modules)}, {secs:.1f} s on {cores} processes"},
+        "parity_vs_oracle": {"objects": n_cpu, "modules": parity},
+    }))
 
 
 def main():
@@ -462,9 +592,13 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--objects", type=int, default=1_000_000, help="objects per GPU per step")
-    ap.add_argument("--modules", default="", help="comma list; default = every pass the library exports")
+    ap.add_argument("--config", default="", choices=["", "c1", "c2", "c3", "c4", "c5"],
+                    help="default: c4 on one GPU, c5 under torchrun")
+    ap.add_argument("--objects", type=int, default=0,
+                    help="c4: objects per GPU (default 10^6); c5: objects of the whole set (default 10^7); c1-c3: objects (default 10,178)")
+    ap.add_argument("--modules", default="", help="comma list; default = every pass of the 434-column table")
     ap.add_argument("--cpu-objects", type=int, default=0, help="CPU sample size (default scales with host cores)")
+    ap.add_argument("--full-cpu", action="store_true", help="c1-c3: run the CPU oracle on the whole set (minutes)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--gp1d-objects", type=int, default=200_000,
                     help="objects of the batch the per-band GP pass (SURVEY 8f row 2) is timed on beside the step; 0 = skip")
@@ -472,6 +606,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.config in ("c1", "c2", "c3"):
+        run_small_config(args)
     else:
         run_gpu_arm(args)
 

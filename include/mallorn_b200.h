@@ -42,7 +42,7 @@ extern "C" {
 #define MLRN_POWERLAW_COLS 27   /* extract_powerlaw_features      scripts/train_v55_powerlaw.py:196 */
 #define MLRN_GP2D_COLS 27       /* extract_multiband_gp_features  multiband_gp.py:347     */
 #define MLRN_GP1D_COLS 21       /* extract_gp_features            gaussian_process.py:251 */
-#define MLRN_RESEARCH_COLS 40   /* extract_research_features      research_features.py:566 (experimental) */
+#define MLRN_RESEARCH_COLS 40   /* extract_research_features      research_features.py:566 */
 #define MLRN_SEGMETA_COLS 22    /* K1 integer outputs per object, see mlrn_store_segments */
 
 typedef struct mlrn_store mlrn_store;   /* packed, device-resident light curves of one batch */
@@ -51,6 +51,10 @@ const char* mlrn_last_error(void);
 int mlrn_version(void);
 int mlrn_device_count(void);            /* number of CUDA devices (0 => every call fails) */
 long long mlrn_launch_count(void);      /* kernels this library has launched so far in the process */
+/* FP64 roofline denominator measured on `device` at call time ("measure with a DFMA micro-benchmark at
+ * bench time"): TFLOP/s (2 x FMA) of a register-resident DFMA loop and of the mma.sync.m8n8k4.f64 loop the GP sweep
+ * issues, 16 warps on every SM.  No reference equivalent (measurement only). */
+int mlrn_measure_fp64(int device, double* dfma_tflops, double* dmma_tflops);
 
 /* K1 -- pack.  Replaces the per-extractor `lightcurves.groupby('object_id')` dict
  * (statistical.py:155, colors.py:365, lightcurve_shape.py:353, physics_based.py:484,

@@ -17,7 +17,7 @@ COLS = {"statistical": 123, "colors": 83, "shape": 65, "tde": 25, "physics": 32,
         "bazin": 52, "powerlaw": 27, "gp2d": 27, "gp1d": 21, "research": 40}
 SEGMETA_COLS = 22
 N_SEG = 7
-MAX_OBS = 1024
+MAX_OBS = 65535       # within-object ranks are uint16; objects above SHORT_LIMIT (512) are staged in a global scratch
 
 
 class MallornNativeError(RuntimeError):
@@ -42,6 +42,7 @@ def lib() -> C.CDLL:
     L.mlrn_version.restype = C.c_int
     L.mlrn_device_count.restype = C.c_int
     L.mlrn_launch_count.restype = C.c_longlong
+    L.mlrn_measure_fp64.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.mlrn_store_create.argtypes = [C.c_int, i64, i32, vp, vp, vp, vp, vp, C.c_int, vp, C.POINTER(vp)]
     L.mlrn_store_destroy.argtypes = [vp]
     L.mlrn_store_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]

@@ -153,7 +153,12 @@ int mlrn_store_create(int device, int64_t n_rows, int32_t n_obj, const int32_t* 
 int mlrn_store_destroy(mlrn_store* s) {
   if (!s) return MLRN_OK;
   DevGuard g(s->device);
-  cudaFree(s->seg_off); cudaFree(s->t); cudaFree(s->flux); cudaFree(s->err); cudaFree(s->rank); cudaFree(s->trank); cudaFree(s->seg_meta); cudaFree(s->ticket);
+  // Passes may have been issued on other streams than the one the store was packed on: wait for the device (what cudaFree
+  // did implicitly), then hand the arrays back to the pool, which keeps them for the next batch.
+  cudaDeviceSynchronize();
+  void* arrays[9] = {s->seg_off, s->t, s->flux, s->err, s->rank, s->trank, s->seg_meta, s->ticket, s->long_list};
+  for (void* a : arrays) if (a) cudaFreeAsync(a, s->stream);
+  cudaGetLastError();
   delete s;
   return MLRN_OK;
 }

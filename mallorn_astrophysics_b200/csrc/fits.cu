@@ -164,6 +164,7 @@ int run_staged(const mlrn_store* s, const P& pol, long long fits, const int* cap
   const int grid0 = (int)(want < full ? (want > 0 ? want : 1) : full);
   long long cap_l = (long long)(carry_frac * (double)fits);
   if (cap_l < 8192) cap_l = 8192;
+  if (cap_l > (4LL << 20)) cap_l = 4LL << 20;         // at most 4 Mi records per buffer (~4 GB for the Bazin job)
   if (cap_l > fits) cap_l = fits;
   const unsigned capacity = (unsigned)(cap_l < 0xffffffffLL ? cap_l : 0xffffffffLL);
   unsigned long long* ctr = nullptr;                  // [MAX_STAGES] tickets, then [MAX_STAGES] carry counts (as unsigned)

@@ -4,13 +4,15 @@
 // the other (gp1d.cuh: four L-BFGS-B starts per band, the symmetric sweep over a packed triangle in shared
 // memory per evaluation) and writes the row.  Shared memory per warp = the optimiser state (lbfgsb.cuh, owned by
 // lane 0) + a scratch sized for bands of up to `cap` valid points; the rare longer band runs the same code with
-// its triangle in a per-warp global scratch (L2-resident).  `cap` trades occupancy against how many bands take
-// the slow path and is chosen by the launcher from the store's longest segment.
+// its triangle in a global scratch (L2-resident): one slot per warp while that fits in 2 GB, otherwise a pool of slots a
+// warp takes for the duration of one band (a 3,000-point band needs 36 MB).  `cap` trades occupancy against how many
+// bands take the slow path and is chosen by the launcher from the store's longest segment.
+// (A register-tiled variant of the sweep -- 4 x 4 tiles of the triangle held in registers -- was prepared in round 1 and
+// measured in round 2: 15.4 k objects/s against 66.5 k for this kernel at 100,000 objects; it was removed.)
 #include <cuda_runtime.h>
 #include <cstdlib>
 #include "store.cuh"
 #include "gp1d.cuh"
-#include "gp1d_tiled.cuh"
 #include "../../include/mallorn_b200.h"
 
 namespace mlrn {
@@ -23,6 +25,7 @@ MLRN_HD size_t gp1d_warp_bytes(int cap) {
 
 __global__ void __launch_bounds__(256, 2) k_gp1d(const long long* __restrict__ seg_off, const double* __restrict__ gt, const double* __restrict__ gf,
                        const double* __restrict__ ge, int n_obj, int cap, int cap_global, double* __restrict__ gscratch,
+                       int n_slots, int* __restrict__ slot_busy,
                        unsigned long long* __restrict__ ticket, double* __restrict__ out, int* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WarpTeam tm;
@@ -31,7 +34,8 @@ __global__ void __launch_bounds__(256, 2) k_gp1d(const long long* __restrict__ s
   LbfgsB<3>* opt = reinterpret_cast<LbfgsB<3>*>(mine);
   double* ctl = reinterpret_cast<double*>(mine + sizeof(LbfgsB<3>));
   double* sbase = ctl + 8;
-  double* gbase = gscratch ? gscratch + ((size_t)blockIdx.x * warps + warp) * (size_t)gp1d_scratch_doubles(cap_global) : nullptr;
+  const int my_warp = blockIdx.x * warps + warp;
+  const bool own_slot = n_slots >= (int)(gridDim.x * warps);          // enough scratch for every warp: no pool
   const int bands[4] = {BG, BR, BI, BZ};
   for (;;) {
     long long o = 0;
@@ -45,60 +49,22 @@ __global__ void __launch_bounds__(256, 2) k_gp1d(const long long* __restrict__ s
       const int n = (int)(seg_off[o * N_SEG + bands[j] + 1] - lo);
       // two instantiations so the common case keeps shared-memory addressing (LDS/STS instead of generic loads)
       if (n <= cap) gp1d_band(tm, gt + lo, gf + lo, ge + lo, n, gp1d_carve(sbase, cap), opt, ctl, res[j]);
-      else gp1d_band(tm, gt + lo, gf + lo, ge + lo, n, gp1d_carve(gbase, cap_global), opt, ctl, res[j]);
-      if (status && tm.rank() == 0) {
-        status[o * GP1D_STATUS + 3 * j] = res[j].nfev; status[o * GP1D_STATUS + 3 * j + 1] = res[j].nit;
-        status[o * GP1D_STATUS + 3 * j + 2] = res[j].winner;
-      }
-    }
-    if (tm.rank() == 0) gp1d_tail(res, out + o * GP1D_COLS);
-  }
-}
-
-// EXPERIMENTAL (MLRN_GP1D_TILED=1): same mapping, but bands of up to 51 valid points evaluate the objective with the
-// matrix in registers (gp1d_tiled.cuh); longer bands fall back to the shared-memory / global sweep above.
-__global__ void __launch_bounds__(128, 3) k_gp1d_tiled(const long long* __restrict__ seg_off, const double* __restrict__ gt,
-                                                        const double* __restrict__ gf, const double* __restrict__ ge, int n_obj, int cap,
-                                                        int cap_global, double* __restrict__ gscratch,
-                                                        unsigned long long* __restrict__ ticket, double* __restrict__ out,
-                                                        int* __restrict__ status) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  WarpTeam tm;
-  const int warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-  unsigned char* mine = smem_raw + (size_t)warp * gp1d_warp_bytes(cap);
-  LbfgsB<3>* opt = reinterpret_cast<LbfgsB<3>*>(mine);
-  double* ctl = reinterpret_cast<double*>(mine + sizeof(LbfgsB<3>));
-  double* sbase = ctl + 8;
-  double* gbase = gscratch ? gscratch + ((size_t)blockIdx.x * warps + warp) * (size_t)gp1d_scratch_doubles(cap_global) : nullptr;
-  const int bands[4] = {BG, BR, BI, BZ};
-  for (;;) {
-    long long o = 0;
-    if (tm.rank() == 0) o = (long long)atomicAdd(ticket, 1ULL);
-    o = __shfl_sync(WarpTeam::FULL, o, 0);
-    if (o >= n_obj) break;
-    Gp1dBandResult res[4];
-#pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
-      const long long lo = seg_off[o * N_SEG + bands[j]];
-      const int nraw = (int)(seg_off[o * N_SEG + bands[j] + 1] - lo);
-      if (nraw <= cap && nraw + 1 <= gp1d_tiled_capacity(3)) {
-        gp1d_clear(res[j]);
-        const Gp1dTiledScratch ts = gp1d_carve_tiled(sbase, cap);
-        double t_range = 0.0, f_std = 1.0;
-        const int n = gp1d_prepare(tm, gt + lo, gf + lo, ge + lo, nraw, ts.x, ts.y, ts.al, t_range, f_std);
-        if (n > 0) {
-          if (n + 1 <= gp1d_tiled_capacity(2)) {
-            WarpLanes<TileRegs<2>> ex;
-            gp1d_optimise(tm, [&](const double* th, double& fv, double* g) {
-              gp1d_objective_tiled<2>(ex, n, ts.x, ts.y, ts.al, ts.vb0, ts.vb1, ts.piv, th, fv, g); }, t_range, f_std, opt, ctl, res[j]);
-          } else {
-            WarpLanes<TileRegs<3>> ex;
-            gp1d_optimise(tm, [&](const double* th, double& fv, double* g) {
-              gp1d_objective_tiled<3>(ex, n, ts.x, ts.y, ts.al, ts.vb0, ts.vb1, ts.piv, th, fv, g); }, t_range, f_std, opt, ctl, res[j]);
+      else {
+        int slot = my_warp;
+        if (!own_slot) {                              // take a slot of the pool for this band
+          if (tm.rank() == 0) {
+            slot = my_warp % n_slots;
+            while (atomicCAS(slot_busy + slot, 0, 1) != 0) { slot = (slot + 1) % n_slots; __nanosleep(200); }
           }
+          slot = __shfl_sync(WarpTeam::FULL, slot, 0);
         }
-      } else if (nraw <= cap) gp1d_band(tm, gt + lo, gf + lo, ge + lo, nraw, gp1d_carve(sbase, cap), opt, ctl, res[j]);
-      else gp1d_band(tm, gt + lo, gf + lo, ge + lo, nraw, gp1d_carve(gbase, cap_global), opt, ctl, res[j]);
+        gp1d_band(tm, gt + lo, gf + lo, ge + lo, n, gp1d_carve(gscratch + (size_t)slot * gp1d_scratch_doubles(cap_global), cap_global), opt, ctl, res[j]);
+        if (!own_slot) {
+          __threadfence();
+          tm.sync();
+          if (tm.rank() == 0) atomicExch(slot_busy + slot, 0);
+        }
+      }
       if (status && tm.rank() == 0) {
         status[o * GP1D_STATUS + 3 * j] = res[j].nfev; status[o * GP1D_STATUS + 3 * j + 1] = res[j].nit;
         status[o * GP1D_STATUS + 3 * j + 2] = res[j].winner;
@@ -119,10 +85,8 @@ int run_gp1d(const mlrn_store* s, double* out_dev, int* status_dev, cudaStream_t
   int dev_smem = 0;
   MLRN_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
   if ((size_t)dev_smem < per_warp) { set_error("gp1d: shared memory too small for one warp"); return MLRN_EINVAL; }
-  const char* tiled_env = getenv("MLRN_GP1D_TILED");
-  const bool tiled = tiled_env && tiled_env[0] == '1';          // experimental register-tiled objective (gp1d_tiled.cuh)
-  auto kernel = tiled ? k_gp1d_tiled : k_gp1d;
-  const int max_warps = tiled ? 4 : 8;                           // launch bounds of the two kernels
+  auto kernel = k_gp1d;
+  const int max_warps = 8;                                       // launch bounds of the kernel
   // CTA shape = the warps-per-CTA that keeps most warps resident on an SM; small CTAs also mean a warp that draws a long
   // object does not hold many others back at the end of the grid
   int per_cta = 1, occ = 1, best = 0;
@@ -140,13 +104,24 @@ int run_gp1d(const mlrn_store* s, double* out_dev, int* status_dev, cudaStream_t
   long long want = ((long long)s->n_obj + per_cta - 1) / per_cta, capg = (long long)s->sm_count * occ;
   const int grid = (int)(want < capg ? want : capg);
   double* gscratch = nullptr;
-  if (longest > cap)
-    MLRN_CUDA(cudaMallocAsync(&gscratch, sizeof(double) * (size_t)gp1d_scratch_doubles(longest) * per_cta * grid, st));
+  int* slot_busy = nullptr;
+  int n_slots = 0;
+  if (longest > cap) {
+    const size_t slot_bytes = sizeof(double) * (size_t)gp1d_scratch_doubles(longest);
+    const long long all = (long long)per_cta * grid;
+    long long fit = (long long)((2ULL << 30) / slot_bytes);     // at most 2 GB of scratch: beyond that the warps share a pool of slots
+    if (fit < 4) fit = 4;
+    n_slots = (int)(fit < all ? fit : all);
+    MLRN_CUDA(cudaMallocAsync(&gscratch, slot_bytes * (size_t)n_slots, st));
+    MLRN_CUDA(cudaMallocAsync(&slot_busy, sizeof(int) * (size_t)n_slots, st));
+    MLRN_CUDA(cudaMemsetAsync(slot_busy, 0, sizeof(int) * (size_t)n_slots, st));
+  }
   MLRN_CUDA(cudaMemsetAsync(s->ticket + 7, 0, sizeof(unsigned long long), st));
-  kernel<<<grid, per_cta * 32, smem, st>>>(s->seg_off, s->t, s->flux, s->err, s->n_obj, cap, longest, gscratch, s->ticket + 7,
-                                           out_dev, status_dev);
+  kernel<<<grid, per_cta * 32, smem, st>>>(s->seg_off, s->t, s->flux, s->err, s->n_obj, cap, longest, gscratch, n_slots, slot_busy,
+                                           s->ticket + 7, out_dev, status_dev);
   cudaError_t e = cudaGetLastError();
   if (gscratch) cudaFreeAsync(gscratch, st);
+  if (slot_busy) cudaFreeAsync(slot_busy, st);
   if (e != cudaSuccess) return cuda_fail(e, "k_gp1d launch");
   count_launch();
   return MLRN_OK;

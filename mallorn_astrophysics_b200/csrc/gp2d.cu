@@ -63,10 +63,15 @@ __host__ __device__ inline size_t gp_fixed_doubles(int np) {
 }
 __host__ __device__ inline size_t gp_tile_doubles(int T) { return (size_t)n_tiles(T) * TT + (size_t)T * VT; }
 __host__ inline size_t gp_smem_bytes(int T, bool tiles_in_smem) {
-  size_t d = gp_fixed_doubles(T * TB) + (size_t)T * VT;        // the V buffer is always in shared memory
-  if (tiles_in_smem) d += (size_t)n_tiles(T) * TT;
+  size_t d = gp_fixed_doubles(T * TB);
+  if (tiles_in_smem) d += (size_t)n_tiles(T) * TT + (size_t)T * VT;      // tiles and V buffer; otherwise both live in the global scratch
   return d * sizeof(double) + 2 * n_tiles(T) + 64;      // + (I, J) byte table of the tiles
 }
+// Longest object the GP handles: 192 tile rows (the (I, J) tables are bytes and the five per-point vectors have to fit in
+// shared memory).  The reference has no such limit in principle (george would factor any N x N matrix); above it the 27
+// columns are NaN and status[2] = GP_TOO_LONG.
+constexpr int GP_T_MAX = 192;
+constexpr int GP_TOO_LONG = -2;
 
 struct GpShared {
   double *tiles, *vbuf;                 // [n_tiles][256], [T][VT]
@@ -481,9 +486,11 @@ k_gp2d(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
     S.Lc = d; d += TT;
     S.Li = d; d += 2 * TT; S.LiT = d; d += 2 * VT; S.w = d; d += 2 * TB;      // double-buffered (look-ahead)
     S.red = d; d += GP_WARPS * 4; S.bc = d; d += 16;
-    S.vbuf = d; d += (size_t)T_cap * VT;
-    if (SMEM_TILES) { S.tiles = d; d += (size_t)n_tiles(T_cap) * TT; }
-    else S.tiles = gscratch + (size_t)blockIdx.x * n_tiles(T_cap) * TT;
+    if (SMEM_TILES) { S.vbuf = d; d += (size_t)T_cap * VT; S.tiles = d; d += (size_t)n_tiles(T_cap) * TT; }
+    else {
+      S.tiles = gscratch + (size_t)blockIdx.x * gp_tile_doubles(T_cap);
+      S.vbuf = S.tiles + (size_t)n_tiles(T_cap) * TT;
+    }
     S.tI = (unsigned char*)d; S.tJ = S.tI + n_tiles(T_cap);
     S.flag = &s_flag;
     // address-space hints: everything carved from the dynamic shared array is shared memory
@@ -494,8 +501,7 @@ k_gp2d(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
     __builtin_assume(__isShared(S.w));
     __builtin_assume(__isShared(S.red)); __builtin_assume(__isShared(S.bc));
     __builtin_assume(__isShared(S.tI)); __builtin_assume(__isShared(S.tJ));
-    __builtin_assume(__isShared(S.vbuf));
-    if (SMEM_TILES) __builtin_assume(__isShared(S.tiles));
+    if (SMEM_TILES) { __builtin_assume(__isShared(S.vbuf)); __builtin_assume(__isShared(S.tiles)); }
   }
   for (int tl = tid; tl < n_tiles(T_cap); tl += GP_THREADS) {
     int I = (int)((sqrt(8.0 * tl + 1.0) - 1.0) * 0.5);
@@ -544,6 +550,11 @@ k_gp2d(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
     if (!mine) continue;
     if (status && tid < 4) status[o * 4 + tid] = (tid == 3) ? n : 0;
     if (n < 10) { if (tid < GP_COLS) row[tid] = qnan(); continue; }       // :66
+    if (n > np_cap) {                                   // beyond GP_T_MAX tile rows
+      if (tid < GP_COLS) row[tid] = qnan();
+      if (status && tid == 0) status[o * 4 + 2] = GP_TOO_LONG;
+      continue;
+    }
     // ---- t -= min(t); flux scale = median |f| over f != 0 (rank counting); y, noise; mean / var
     double red[4] = {0.0, 0.0, 0.0, 0.0};
     {
@@ -678,7 +689,9 @@ extern "C" void mlrn_gp_phase_cycles(unsigned long long* out8, int reset) {
 
 int run_gp2d(const mlrn_store* s, double* out_dev, int* status_dev, cudaStream_t st) {
   if (s->n_obj == 0) return MLRN_OK;
-  const int T_need = (s->max_obs + TB - 1) / TB > 1 ? (s->max_obs + TB - 1) / TB : 1;
+  int T_need = (s->max_obs + TB - 1) / TB > 1 ? (s->max_obs + TB - 1) / TB : 1;
+  const bool any_beyond = T_need > T_SMEM_MAX;
+  if (T_need > GP_T_MAX) T_need = GP_T_MAX;
   const int T1 = T_need < T_SMEM_MAX ? T_need : T_SMEM_MAX;
   const size_t smem1 = gp_smem_bytes(T1, true), smem2 = gp_smem_bytes(T_need, false);
   MLRN_CUDA(cudaFuncSetAttribute(k_gp2d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
@@ -689,19 +702,28 @@ int run_gp2d(const mlrn_store* s, double* out_dev, int* status_dev, cudaStream_t
   if (occ1 < 1) occ1 = 1;
   if (occ2 < 1) occ2 = 1;
   auto grid_for = [&](int occ) { long long g = (long long)s->sm_count * occ; return (int)(s->n_obj < g ? s->n_obj : g); };
-  const int grid1 = grid_for(occ1), grid2 = grid_for(occ2), gmax = grid1 > grid2 ? grid1 : grid2;
+  const int grid1 = grid_for(occ1);
+  int grid2 = 0;
+  const size_t cache1 = sizeof(double) * 2 * (size_t)n_tiles(T1) * TT, cache2 = sizeof(double) * 2 * (size_t)n_tiles(T_need) * TT;
+  const size_t scratch2 = sizeof(double) * gp_tile_doubles(T_need);
+  if (any_beyond) {                                     // objects beyond the shared-memory capacity: tiles in an L2-resident scratch
+    grid2 = grid_for(occ2);
+    const long long fit = (long long)((6ULL << 30) / (cache2 + scratch2));     // at most 6 GB of per-CTA scratch (a 3,000-point object needs 109 MB)
+    if (grid2 > fit) grid2 = (int)(fit > 1 ? fit : 1);
+  }
+  const size_t cache_bytes = cache1 * grid1 > cache2 * grid2 ? cache1 * grid1 : cache2 * grid2;
   double* cache = nullptr;                              // s / exp(-s) of the current evaluation, per CTA (L2-resident)
-  MLRN_CUDA(cudaMallocAsync(&cache, sizeof(double) * 2 * (size_t)n_tiles(T_need) * TT * gmax, st));
+  MLRN_CUDA(cudaMallocAsync(&cache, cache_bytes, st));
   MLRN_CUDA(cudaMemsetAsync(s->ticket + 2, 0, 2 * sizeof(unsigned long long), st));
   k_gp2d<true><<<grid1, GP_THREADS, smem1, st>>>(s->seg_off, s->t, s->flux, s->err, s->rank, s->n_obj, T1, 0, T1 * TB,
                                                  nullptr, cache, s->ticket + 2, out_dev, status_dev);
   MLRN_CUDA(cudaGetLastError());
   count_launch();
-  if (T_need > T_SMEM_MAX) {                            // objects beyond the shared-memory capacity: tiles in an L2-resident scratch
+  if (any_beyond) {
     double* scratch = nullptr;
-    MLRN_CUDA(cudaMallocAsync(&scratch, sizeof(double) * (size_t)n_tiles(T_need) * TT * grid2, st));
+    MLRN_CUDA(cudaMallocAsync(&scratch, scratch2 * grid2, st));
     k_gp2d<false><<<grid2, GP_THREADS, smem2, st>>>(s->seg_off, s->t, s->flux, s->err, s->rank, s->n_obj, T_need,
-                                                   T1 * TB + 1, T_need * TB, scratch, cache, s->ticket + 3, out_dev, status_dev);
+                                                   T1 * TB + 1, 0x7fffffff, scratch, cache, s->ticket + 3, out_dev, status_dev);
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(scratch, st);
     if (e != cudaSuccess) { cudaFreeAsync(cache, st); return cuda_fail(e, "k_gp2d<global> launch"); }

@@ -15,7 +15,19 @@ namespace mlrn {
 
 constexpr int N_SEG = 7;        // ugrizy + unknown
 constexpr int N_BAND = 6;
-constexpr int MAX_OBS = 1024;   // per-object cap (shared-memory staging); pack rejects larger objects
+constexpr int MAX_OBS = 65535;     // per-object cap: within-object ranks are stored as uint16; pack rejects larger objects
+constexpr int SHORT_LIMIT = 512;   // objects up to this many observations are staged in shared memory, longer ones in a global scratch
+
+// Which objects a launch of a staging kernel (K1 arrange, K2, K3, research) handles and where their staging area lives.
+// The reference takes any length (statistical.py:163-190); survey light curves have ~150 points, so the shared-memory
+// launch is sized by the longest SHORT object of the batch and the rare longer ones run the same code in a second launch
+// over the list pack.cu makes of them, with the per-warp staging area in global memory (L2-resident).
+struct ObjClass {
+  const int* list;           // long launch: the objects to handle; nullptr: every object not above n_hi
+  int count;                 // entries of list, or n_obj
+  int n_hi;                  // short launch: objects with more observations are left to the long launch
+  unsigned char* scratch;    // long launch: staging areas [warps of the grid][bytes per warp]; nullptr: shared memory
+};
 enum Band { BU = 0, BG = 1, BR = 2, BI = 3, BZ = 4, BY = 5, BX = 6 };
 
 struct ObjView {

@@ -45,23 +45,29 @@ __device__ __forceinline__ int obj_total(const int* seg_cnt, int64_t o) {
 }
 
 // block sum of per-object totals -> partial[blockIdx]; also the largest object
+// flags: [0] largest object, [1] error flag of k_arrange, [2] largest segment, [4] largest SHORT object, [5] number of long
+// objects (their indices go to long_list)
 __global__ void k_obj_partial(const int* __restrict__ seg_cnt, int n_obj, long long* __restrict__ partial,
-                              int* __restrict__ max_obs) {
+                              int* __restrict__ max_obs, int* __restrict__ long_list) {
   __shared__ long long ws[SCAN_THREADS / 32];
   int64_t base = (int64_t)blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
-  long long s = 0; int mx = 0, ms = 0;
+  long long s = 0; int mx = 0, ms = 0, mshort = 0;
   for (int k = 0; k < SCAN_ITEMS; ++k) {
     int64_t o = base + k;
     if (o < n_obj) {
       int c = obj_total(seg_cnt, o); s += c; mx = max(mx, c);
+      if (c <= SHORT_LIMIT) mshort = max(mshort, c);
+      else long_list[atomicAdd(max_obs + 5, 1)] = (int)o;
       for (int b = 0; b < N_SEG; ++b) ms = max(ms, seg_cnt[o * N_SEG + b]);
     }
   }
   for (int d = 16; d > 0; d >>= 1) {
     s += __shfl_xor_sync(0xffffffffu, s, d); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-    ms = max(ms, __shfl_xor_sync(0xffffffffu, ms, d));
+    ms = max(ms, __shfl_xor_sync(0xffffffffu, ms, d)); mshort = max(mshort, __shfl_xor_sync(0xffffffffu, mshort, d));
   }
-  if ((threadIdx.x & 31) == 0) { ws[threadIdx.x >> 5] = s; atomicMax(max_obs, mx); atomicMax(max_obs + 2, ms); }
+  if ((threadIdx.x & 31) == 0) {
+    ws[threadIdx.x >> 5] = s; atomicMax(max_obs, mx); atomicMax(max_obs + 2, ms); atomicMax(max_obs + 4, mshort);
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     long long tot = 0;
@@ -182,11 +188,12 @@ __host__ __device__ inline size_t arrange_bytes_per_warp(int np) {
 __global__ void __launch_bounds__(ARR_WARPS * 32)
 k_arrange(const uint8_t* __restrict__ band_in, const double* __restrict__ t_in, const double* __restrict__ f_in,
           const double* __restrict__ e_in, const int* __restrict__ rowid, const long long* __restrict__ seg_off,
-          int n_obj, int np, double* __restrict__ t_out, double* __restrict__ f_out, double* __restrict__ e_out,
+          ObjClass cls, int np, double* __restrict__ t_out, double* __restrict__ f_out, double* __restrict__ e_out,
           unsigned short* __restrict__ rank_out, unsigned short* __restrict__ trank_out, int* __restrict__ seg_meta, int* __restrict__ err_flag) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char* base = smem + (size_t)warp * arrange_bytes_per_warp(np);
+  unsigned char* base = cls.scratch ? cls.scratch + ((size_t)blockIdx.x * ARR_WARPS + warp) * arrange_bytes_per_warp(np)
+                                    : smem + (size_t)warp * arrange_bytes_per_warp(np);
   double* tt = (double*)base;
   double* ff = tt + np;
   double* fs = ff + np;
@@ -194,11 +201,13 @@ k_arrange(const uint8_t* __restrict__ band_in, const double* __restrict__ t_in, 
   unsigned short* perm = (unsigned short*)(ids + np);
   unsigned short* bb = perm + np;
 
-  for (int64_t o = (int64_t)blockIdx.x * ARR_WARPS + warp; o < n_obj; o += (int64_t)gridDim.x * ARR_WARPS) {
+  for (int64_t slot = (int64_t)blockIdx.x * ARR_WARPS + warp; slot < cls.count; slot += (int64_t)gridDim.x * ARR_WARPS) {
+    const int64_t o = cls.list ? cls.list[slot] : slot;
     const long long* so = seg_off + o * N_SEG;
     const long long gbase = so[0];
     const int n = (int)(so[N_SEG] - gbase);
     int* meta = seg_meta + o * MLRN_SEGMETA_COLS;
+    if (!cls.list && n > cls.n_hi) continue;          // a long object: the second launch's
     if (n > MAX_OBS) { if (lane == 0) atomicMax(err_flag, n); continue; }
     int off[N_SEG + 1];
     for (int b = 0; b <= N_SEG; ++b) off[b] = (int)(so[b] - gbase);
@@ -284,6 +293,7 @@ k_arrange(const uint8_t* __restrict__ band_in, const double* __restrict__ t_in, 
 int pack_device(mlrn_store* s, int64_t n_rows, const int32_t* obj, const uint8_t* band, const double* t,
                 const double* flux, const double* err, cudaStream_t st) {
   const int n_obj = s->n_obj;
+  s->stream = st;                       // the store's arrays are stream-ordered allocations (cached by the pool across batches)
   const int64_t n_seg = (int64_t)n_obj * N_SEG;
   const int n_blocks = (n_obj + SCAN_CHUNK - 1) / SCAN_CHUNK;
   int *seg_cnt = nullptr, *cursor = nullptr, *rowid = nullptr, *flags = nullptr;
@@ -291,18 +301,19 @@ int pack_device(mlrn_store* s, int64_t n_rows, const int32_t* obj, const uint8_t
   MLRN_CUDA(cudaMallocAsync(&seg_cnt, sizeof(int) * (size_t)(n_seg > 0 ? n_seg : 1), st));
   MLRN_CUDA(cudaMallocAsync(&cursor, sizeof(int) * (size_t)(n_obj > 0 ? n_obj : 1), st));
   MLRN_CUDA(cudaMallocAsync(&partial, sizeof(long long) * (size_t)(n_blocks + 1), st));
-  MLRN_CUDA(cudaMallocAsync(&flags, sizeof(int) * 4, st));
+  MLRN_CUDA(cudaMallocAsync(&flags, sizeof(int) * 8, st));
+  MLRN_CUDA(cudaMallocAsync(&s->long_list, sizeof(int) * (size_t)(n_obj > 0 ? n_obj : 1), st));
   MLRN_CUDA(cudaMemsetAsync(seg_cnt, 0, sizeof(int) * (size_t)(n_seg > 0 ? n_seg : 1), st));
   MLRN_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int) * (size_t)(n_obj > 0 ? n_obj : 1), st));
-  MLRN_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 4, st));
-  MLRN_CUDA(cudaMalloc(&s->seg_off, sizeof(long long) * (size_t)(n_seg + 1)));
-  MLRN_CUDA(cudaMalloc(&s->seg_meta, sizeof(int32_t) * (size_t)(n_obj > 0 ? n_obj : 1) * MLRN_SEGMETA_COLS));
-  MLRN_CUDA(cudaMalloc(&s->ticket, sizeof(unsigned long long) * 8));
+  MLRN_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 8, st));
+  MLRN_CUDA(cudaMallocAsync(&s->seg_off, sizeof(long long) * (size_t)(n_seg + 1), st));
+  MLRN_CUDA(cudaMallocAsync(&s->seg_meta, sizeof(int32_t) * (size_t)(n_obj > 0 ? n_obj : 1) * MLRN_SEGMETA_COLS, st));
+  MLRN_CUDA(cudaMallocAsync(&s->ticket, sizeof(unsigned long long) * 8, st));
 
   const int row_grid = (int)((n_rows + 255) / 256 < (int64_t)s->sm_count * 16 ? (n_rows + 255) / 256 : (int64_t)s->sm_count * 16);
   if (n_rows > 0) { k_count<<<row_grid > 0 ? row_grid : 1, 256, 0, st>>>(obj, band, n_rows, n_obj, seg_cnt); count_launch(); }
   if (n_obj > 0) {
-    k_obj_partial<<<n_blocks, SCAN_THREADS, 0, st>>>(seg_cnt, n_obj, partial, flags);
+    k_obj_partial<<<n_blocks, SCAN_THREADS, 0, st>>>(seg_cnt, n_obj, partial, flags, s->long_list);
     k_scan_partials<<<1, 1024, 0, st>>>(partial, n_blocks);
     k_obj_offsets<<<n_blocks, SCAN_THREADS, 0, st>>>(seg_cnt, n_obj, partial, s->seg_off);
     count_launch(3);
@@ -310,37 +321,51 @@ int pack_device(mlrn_store* s, int64_t n_rows, const int32_t* obj, const uint8_t
     MLRN_CUDA(cudaMemsetAsync(s->seg_off, 0, sizeof(long long), st));
   }
   MLRN_CUDA(cudaGetLastError());
-  long long total = 0; int h_flags[4] = {0, 0, 0, 0};
+  long long total = 0; int h_flags[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   MLRN_CUDA(cudaMemcpyAsync(&total, s->seg_off + n_seg, sizeof(long long), cudaMemcpyDeviceToHost, st));
-  MLRN_CUDA(cudaMemcpyAsync(h_flags, flags, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+  MLRN_CUDA(cudaMemcpyAsync(h_flags, flags, sizeof(int) * 8, cudaMemcpyDeviceToHost, st));
   MLRN_CUDA(cudaStreamSynchronize(st));
   s->n_rows = total;
   s->max_obs = h_flags[0];
   s->max_seg = h_flags[2];
+  s->max_short = h_flags[4];
+  s->n_long = h_flags[5];
   if (s->max_obs > MAX_OBS) {
     cudaFreeAsync(seg_cnt, st); cudaFreeAsync(cursor, st); cudaFreeAsync(partial, st); cudaFreeAsync(flags, st);
     set_error("an object has " + std::to_string(s->max_obs) + " observations; the per-object cap is " + std::to_string(MAX_OBS));
     return MLRN_ETOOLONG;
   }
   const size_t nr = (size_t)(total > 0 ? total : 1);
-  MLRN_CUDA(cudaMalloc(&s->t, sizeof(double) * nr));
-  MLRN_CUDA(cudaMalloc(&s->flux, sizeof(double) * nr));
-  MLRN_CUDA(cudaMalloc(&s->err, sizeof(double) * nr));
-  MLRN_CUDA(cudaMalloc(&s->rank, sizeof(unsigned short) * nr));
-  MLRN_CUDA(cudaMalloc(&s->trank, sizeof(unsigned short) * nr));
+  MLRN_CUDA(cudaMallocAsync(&s->t, sizeof(double) * nr, st));
+  MLRN_CUDA(cudaMallocAsync(&s->flux, sizeof(double) * nr, st));
+  MLRN_CUDA(cudaMallocAsync(&s->err, sizeof(double) * nr, st));
+  MLRN_CUDA(cudaMallocAsync(&s->rank, sizeof(unsigned short) * nr, st));
+  MLRN_CUDA(cudaMallocAsync(&s->trank, sizeof(unsigned short) * nr, st));
   MLRN_CUDA(cudaMallocAsync(&rowid, sizeof(int) * nr, st));
   if (n_obj > 0) {
     // k_arrange is the only writer of seg_meta, so it also runs for a batch without rows (every object then gets
     // the count-0 / position -1 pattern and no input column is touched)
     if (n_rows > 0) k_scatter<<<row_grid > 0 ? row_grid : 1, 256, 0, st>>>(obj, n_rows, n_obj, s->seg_off, cursor, rowid);
-    const int np = next_pow2(s->max_obs > 1 ? s->max_obs : 1);
+    // short objects: staging in shared memory sized by the longest of them
+    const int np = next_pow2(s->max_short > 1 ? s->max_short : 1);
     const size_t smem = arrange_bytes_per_warp(np) * ARR_WARPS;
     MLRN_CUDA(cudaFuncSetAttribute(k_arrange, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = (n_obj + ARR_WARPS - 1) / ARR_WARPS;
     const int cap = s->sm_count * 8;
     if (grid > cap) grid = cap;
-    k_arrange<<<grid, ARR_WARPS * 32, smem, st>>>(band, t, flux, err, rowid, s->seg_off, n_obj, np, s->t, s->flux,
-                                                   s->err, s->rank, s->trank, s->seg_meta, flags + 1);
+    k_arrange<<<grid, ARR_WARPS * 32, smem, st>>>(band, t, flux, err, rowid, s->seg_off, ObjClass{nullptr, n_obj, SHORT_LIMIT, nullptr}, np,
+                                                   s->t, s->flux, s->err, s->rank, s->trank, s->seg_meta, flags + 1);
+    if (s->n_long > 0) {                              // long objects: the same code, staging in a global scratch
+      const int npl = next_pow2(s->max_obs);
+      int gl = (s->n_long + ARR_WARPS - 1) / ARR_WARPS;
+      if (gl > s->sm_count * 2) gl = s->sm_count * 2;
+      unsigned char* scratch = nullptr;
+      MLRN_CUDA(cudaMallocAsync(&scratch, arrange_bytes_per_warp(npl) * ARR_WARPS * (size_t)gl, st));
+      k_arrange<<<gl, ARR_WARPS * 32, 0, st>>>(band, t, flux, err, rowid, s->seg_off, ObjClass{s->long_list, s->n_long, MAX_OBS, scratch}, npl,
+                                                s->t, s->flux, s->err, s->rank, s->trank, s->seg_meta, flags + 1);
+      cudaFreeAsync(scratch, st);
+      count_launch();
+    }
     count_launch(2);
   }
   MLRN_CUDA(cudaGetLastError());

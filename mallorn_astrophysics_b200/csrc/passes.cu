@@ -33,13 +33,14 @@ template <int PASS>
 __global__ void __launch_bounds__(PASS_WARPS * 32)
 k_pass(const long long* __restrict__ seg_off, const double* __restrict__ gt, const double* __restrict__ gf,
        const double* __restrict__ ge, const unsigned short* __restrict__ grank, const double* __restrict__ z,
-       int n_obj, int np, double* __restrict__ out) {
+       ObjClass cls, int np, double* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int NS = PassTraits<PASS>::scratch;
   constexpr int COLS = PassTraits<PASS>::cols;
   WarpTeam tm;
   const int warp = threadIdx.x >> 5;
-  unsigned char* base = smem + (size_t)warp * pass_bytes_per_warp(np, NS);
+  unsigned char* base = cls.scratch ? cls.scratch + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * pass_bytes_per_warp(np, NS)
+                                    : smem + (size_t)warp * pass_bytes_per_warp(np, NS);
   double* row = (double*)base;
   double* st = row + ROW_CAP;
   double* sf = st + np;
@@ -48,7 +49,9 @@ k_pass(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
   unsigned short* srank = (unsigned short*)(scr + (size_t)NS * np);
 
   const int nwarps = blockDim.x >> 5;     // 4, or fewer when long objects need more scratch per warp
-  for (long long o = (long long)blockIdx.x * nwarps + warp; o < n_obj; o += (long long)gridDim.x * nwarps) {
+  for (long long slot = (long long)blockIdx.x * nwarps + warp; slot < cls.count; slot += (long long)gridDim.x * nwarps) {
+    const long long o = cls.list ? cls.list[slot] : slot;
+    if (!cls.list && (int)(seg_off[(o + 1) * N_SEG] - seg_off[o * N_SEG]) > cls.n_hi) continue;     // a long object: the second launch's
     ObjView v;
     stage_object(tm, seg_off, gt, gf, ge, grank, o, st, sf, se, srank, v);
     if (PASS == PASS_COLOR) color_row(tm, v, scr, scr + np, row);
@@ -65,7 +68,8 @@ k_pass(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
 template <int PASS>
 int launch_pass(const mlrn_store* s, const double* z, double* out, cudaStream_t st) {
   if (s->n_obj == 0) return MLRN_OK;
-  const int np = next_pow2(s->max_obs > 64 ? s->max_obs : 64);   // scratch also holds small fixed tables
+  // short objects: shared-memory staging sized by the longest of them
+  const int np = next_pow2(s->max_short > 64 ? s->max_short : 64);   // scratch also holds small fixed tables
   int warps = PASS_WARPS;
   while (warps > 1 && pass_bytes_per_warp(np, PassTraits<PASS>::scratch) * warps > 200 * 1024) warps >>= 1;
   const size_t smem = pass_bytes_per_warp(np, PassTraits<PASS>::scratch) * warps;
@@ -76,9 +80,21 @@ int launch_pass(const mlrn_store* s, const double* z, double* out, cudaStream_t 
   long long want = ((long long)s->n_obj + warps - 1) / warps;
   long long cap = (long long)s->sm_count * per_sm;
   int grid = (int)(want < cap ? want : cap);
-  k_pass<PASS><<<grid, warps * 32, smem, st>>>(s->seg_off, s->t, s->flux, s->err, s->rank, z, s->n_obj, np, out);
+  k_pass<PASS><<<grid, warps * 32, smem, st>>>(s->seg_off, s->t, s->flux, s->err, s->rank, z, ObjClass{nullptr, s->n_obj, SHORT_LIMIT, nullptr}, np, out);
   MLRN_CUDA(cudaGetLastError());
   count_launch();
+  if (s->n_long > 0) {                                // long objects: the same code, staging in a per-warp global scratch
+    const int npl = next_pow2(s->max_obs);
+    int gl = (s->n_long + PASS_WARPS - 1) / PASS_WARPS;
+    if (gl > s->sm_count * 2) gl = s->sm_count * 2;
+    unsigned char* scratch = nullptr;
+    MLRN_CUDA(cudaMallocAsync(&scratch, pass_bytes_per_warp(npl, PassTraits<PASS>::scratch) * PASS_WARPS * (size_t)gl, st));
+    k_pass<PASS><<<gl, PASS_WARPS * 32, 0, st>>>(s->seg_off, s->t, s->flux, s->err, s->rank, z, ObjClass{s->long_list, s->n_long, MAX_OBS, scratch}, npl, out);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(scratch, st);
+    if (e != cudaSuccess) return cuda_fail(e, "k_pass (long objects) launch");
+    count_launch();
+  }
   return MLRN_OK;
 }
 

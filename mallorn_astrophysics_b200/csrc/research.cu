@@ -26,11 +26,12 @@ __host__ __device__ inline size_t research_bytes_per_warp(int np) {
 __global__ void __launch_bounds__(RESEARCH_WARPS * 32)
 k_research(const long long* __restrict__ seg_off, const double* __restrict__ gt, const double* __restrict__ gf,
            const double* __restrict__ ge, const unsigned short* __restrict__ grank, const double* __restrict__ z,
-           int n_obj, int np, double* __restrict__ gridbuf, double* __restrict__ out) {
+           ObjClass cls, int np, double* __restrict__ gridbuf, double* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem[];
   WarpTeam tm;
   const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  unsigned char* base = smem + (size_t)warp * research_bytes_per_warp(np);
+  unsigned char* base = cls.scratch ? cls.scratch + ((size_t)blockIdx.x * nwarps + warp) * research_bytes_per_warp(np)
+                                    : smem + (size_t)warp * research_bytes_per_warp(np);
   double* row = (double*)base;
   double* wav = row + RESEARCH_ROW_CAP;
   double* st = wav + MHPS_WAVELET_CAP;
@@ -39,7 +40,9 @@ k_research(const long long* __restrict__ seg_off, const double* __restrict__ gt,
   double* scr = se + np;
   unsigned short* srank = (unsigned short*)(scr + (size_t)3 * np);
   double* grid = gridbuf + ((size_t)blockIdx.x * nwarps + warp) * RESEARCH_GRID_CAP;
-  for (long long o = (long long)blockIdx.x * nwarps + warp; o < n_obj; o += (long long)gridDim.x * nwarps) {
+  for (long long slot = (long long)blockIdx.x * nwarps + warp; slot < cls.count; slot += (long long)gridDim.x * nwarps) {
+    const long long o = cls.list ? cls.list[slot] : slot;
+    if (!cls.list && (int)(seg_off[(o + 1) * N_SEG] - seg_off[o * N_SEG]) > cls.n_hi) continue;     // a long object: the second launch's
     ObjView v;
     stage_object(tm, seg_off, gt, gf, ge, grank, o, st, sf, se, srank, v);
     research_row(tm, v, z ? z[o] : qnan(), scr, scr + np, scr + 2 * np, grid, RESEARCH_GRID_CAP, wav, row);
@@ -54,7 +57,7 @@ k_research(const long long* __restrict__ seg_off, const double* __restrict__ gt,
 
 int run_research(const mlrn_store* s, const double* z_dev, double* out_dev, cudaStream_t st) {
   if (s->n_obj == 0) return MLRN_OK;
-  const int np = next_pow2(s->max_obs > 64 ? s->max_obs : 64);
+  const int np = next_pow2(s->max_short > 64 ? s->max_short : 64);
   int warps = RESEARCH_WARPS;
   while (warps > 1 && research_bytes_per_warp(np) * warps > 200 * 1024) warps >>= 1;
   const size_t smem = research_bytes_per_warp(np) * warps;
@@ -64,13 +67,30 @@ int run_research(const mlrn_store* s, const double* z_dev, double* out_dev, cuda
   if (per_sm < 1) per_sm = 1;
   long long want = ((long long)s->n_obj + warps - 1) / warps, cap = (long long)s->sm_count * per_sm;
   const int grid = (int)(want < cap ? want : cap);
+  int gl = 0, npl = 0;
+  if (s->n_long > 0) {
+    npl = next_pow2(s->max_obs);
+    gl = (s->n_long + RESEARCH_WARPS - 1) / RESEARCH_WARPS;
+    if (gl > s->sm_count * 2) gl = s->sm_count * 2;
+  }
+  const size_t grid_warps = (size_t)warps * grid > (size_t)RESEARCH_WARPS * gl ? (size_t)warps * grid : (size_t)RESEARCH_WARPS * gl;
   double* gridbuf = nullptr;
-  MLRN_CUDA(cudaMallocAsync(&gridbuf, sizeof(double) * (size_t)RESEARCH_GRID_CAP * warps * grid, st));
-  k_research<<<grid, warps * 32, smem, st>>>(s->seg_off, s->t, s->flux, s->err, s->rank, z_dev, s->n_obj, np, gridbuf, out_dev);
+  MLRN_CUDA(cudaMallocAsync(&gridbuf, sizeof(double) * (size_t)RESEARCH_GRID_CAP * grid_warps, st));
+  k_research<<<grid, warps * 32, smem, st>>>(s->seg_off, s->t, s->flux, s->err, s->rank, z_dev, ObjClass{nullptr, s->n_obj, SHORT_LIMIT, nullptr}, np, gridbuf, out_dev);
   cudaError_t e = cudaGetLastError();
+  count_launch();
+  if (e == cudaSuccess && gl > 0) {                   // long objects: staging in a per-warp global scratch
+    unsigned char* scratch = nullptr;
+    e = cudaMallocAsync(&scratch, research_bytes_per_warp(npl) * RESEARCH_WARPS * (size_t)gl, st);
+    if (e == cudaSuccess) {
+      k_research<<<gl, RESEARCH_WARPS * 32, 0, st>>>(s->seg_off, s->t, s->flux, s->err, s->rank, z_dev, ObjClass{s->long_list, s->n_long, MAX_OBS, scratch}, npl, gridbuf, out_dev);
+      e = cudaGetLastError();
+      cudaFreeAsync(scratch, st);
+      count_launch();
+    }
+  }
   cudaFreeAsync(gridbuf, st);
   if (e != cudaSuccess) return cuda_fail(e, "k_research launch");
-  count_launch();
   return MLRN_OK;
 }
 

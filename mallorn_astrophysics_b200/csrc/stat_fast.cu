@@ -174,24 +174,27 @@ __host__ __device__ inline size_t sf_warp_doubles(int cap) { return 5 * (size_t)
 
 __global__ void __launch_bounds__(SF_WARPS_MAX * 32)
 k_stat(const long long* __restrict__ seg_off, const double* __restrict__ gt, const double* __restrict__ gf,
-       const double* __restrict__ ge, const unsigned short* __restrict__ gtrank, int n_obj, int cap,
+       const double* __restrict__ ge, const unsigned short* __restrict__ gtrank, ObjClass cls, int cap,
        double* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  double* row = (double*)smem + (size_t)warp * sf_warp_doubles(cap);
+  double* row = cls.scratch ? (double*)cls.scratch + ((size_t)blockIdx.x * nwarps + warp) * sf_warp_doubles(cap)
+                            : (double*)smem + (size_t)warp * sf_warp_doubles(cap);
   double* st = row + SF_ROW;
   double* sf = st + cap;
   double* se = sf + cap;        // errors during the band phase, time-ordered times afterwards
   double* run = se + cap;       // seven sorted runs, back to back (same offsets as the segments)
   double* tf = run + cap;       // time-ordered fluxes; scratch for the sort of long bands before that
   double* mrg = st;             // merged sorted fluxes: the staged times are dead once the time-ordered copy exists
-  for (long long o = (long long)blockIdx.x * nwarps + warp; o < n_obj; o += (long long)gridDim.x * nwarps) {
+  for (long long slot = (long long)blockIdx.x * nwarps + warp; slot < cls.count; slot += (long long)gridDim.x * nwarps) {
+    const long long o = cls.list ? cls.list[slot] : slot;
     const long long* so = seg_off + o * N_SEG;
     const long long base = so[0];
     int off[N_SEG + 1];
 #pragma unroll
     for (int b = 0; b <= N_SEG; ++b) off[b] = (int)(so[b] - base);
     const int n = off[N_SEG];
+    if (!cls.list && n > cls.n_hi) continue;          // a long object: the second launch's
     unsigned short trk[8];                                  // time ranks of this lane's observations (n <= 256 fast path)
     for (int i = lane, q = 0; i < n; i += 32, ++q) {
       st[i] = gt[base + i]; sf[i] = gf[base + i]; se[i] = ge[base + i];
@@ -296,12 +299,20 @@ k_stat(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
 
 }  // namespace
 
+// staging capacity per warp for objects of at most `longest` observations with segments of at most `seg`: the object, and
+// room for the power-of-two padding of the long-band sort
+static int stat_cap(int longest, int seg) {
+  int cap = (longest + 7) & ~7;
+  if (cap < 32) cap = 32;
+  if (seg > 64 && cap < next_pow2(seg)) cap = next_pow2(seg);
+  return cap;
+}
+
 int run_stat(const mlrn_store* s, double* out_dev, cudaStream_t st) {
   if (s->n_obj == 0) return MLRN_OK;
-  // staging capacity per warp: the longest object, and room for the power-of-two padding of the long-band sort
-  int cap = (s->max_obs + 7) & ~7;
-  if (cap < 32) cap = 32;
-  if (s->max_seg > 64 && cap < next_pow2(s->max_seg)) cap = next_pow2(s->max_seg);
+  // short objects: shared-memory staging sized by the longest of them (not by the longest object of the batch: one
+  // 3,000-point object used to push every warp's slice to the point where a single warp fitted on an SM)
+  const int cap = stat_cap(s->max_short, s->max_seg < s->max_short ? s->max_seg : s->max_short);
   int warps = 4;
   while (warps > 1 && sf_warp_doubles(cap) * sizeof(double) * warps > 56 * 1024) warps >>= 1;
   const size_t smem = sf_warp_doubles(cap) * sizeof(double) * warps;
@@ -312,9 +323,21 @@ int run_stat(const mlrn_store* s, double* out_dev, cudaStream_t st) {
   long long want = ((long long)s->n_obj + warps - 1) / warps;
   long long capg = (long long)s->sm_count * per_sm;
   const int grid = (int)(want < capg ? want : capg);
-  k_stat<<<grid, warps * 32, smem, st>>>(s->seg_off, s->t, s->flux, s->err, s->trank, s->n_obj, cap, out_dev);
+  k_stat<<<grid, warps * 32, smem, st>>>(s->seg_off, s->t, s->flux, s->err, s->trank, ObjClass{nullptr, s->n_obj, SHORT_LIMIT, nullptr}, cap, out_dev);
   MLRN_CUDA(cudaGetLastError());
   count_launch();
+  if (s->n_long > 0) {                                // long objects: staging in a per-warp global scratch
+    const int capl = stat_cap(s->max_obs, s->max_seg);
+    int gl = (s->n_long + 3) / 4;
+    if (gl > s->sm_count * 2) gl = s->sm_count * 2;
+    unsigned char* scratch = nullptr;
+    MLRN_CUDA(cudaMallocAsync(&scratch, sf_warp_doubles(capl) * sizeof(double) * 4 * (size_t)gl, st));
+    k_stat<<<gl, 4 * 32, 0, st>>>(s->seg_off, s->t, s->flux, s->err, s->trank, ObjClass{s->long_list, s->n_long, MAX_OBS, scratch}, capl, out_dev);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(scratch, st);
+    if (e != cudaSuccess) return cuda_fail(e, "k_stat (long objects) launch");
+    count_launch();
+  }
   return MLRN_OK;
 }
 

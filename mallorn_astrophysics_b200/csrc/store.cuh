@@ -10,6 +10,9 @@ struct mlrn_store {
   int32_t n_obj = 0;
   int32_t max_obs = 0;      // largest per-object count
   int32_t max_seg = 0;      // largest (object, band) segment
+  int32_t max_short = 0;    // largest object among those with at most SHORT_LIMIT observations
+  int32_t n_long = 0;       // objects above SHORT_LIMIT ...
+  int* long_list = nullptr; // ... and their indices [n_long] (order unspecified)
   int32_t sm_count = 148;
   long long* seg_off = nullptr;     // [n_obj*7 + 1]
   double* t = nullptr;              // [n_rows]
@@ -18,7 +21,8 @@ struct mlrn_store {
   unsigned short* rank = nullptr;   // [n_rows] position of the row inside its object in FILE order
   unsigned short* trank = nullptr;  // [n_rows] position inside its object in (time, file rank) order over ALL bands
   int32_t* seg_meta = nullptr;      // [n_obj*22]
-  unsigned long long* ticket = nullptr;   // [8] work counters of the fit / GP passes (one per launch)
+  unsigned long long* ticket = nullptr;   // [8] work counters of the GP passes (one per launch)
+  cudaStream_t stream = nullptr;          // the stream the store was packed on: its arrays are stream-ordered allocations of it
 };
 
 namespace mlrn {

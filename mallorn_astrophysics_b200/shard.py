@@ -3,8 +3,11 @@
 Objects are independent: each rank packs and featurises a contiguous range of the
 dense object index, chosen so the ranges carry equal *cost* (observation counts by default; the GP pass
 costs ~N^3 per object, so ``cost='cubic'`` balances that instead).  Nothing is exchanged during compute;
-at the end one ``all_gather_into_tensor`` of the padded ``[rows_max, n_cols]`` float64 table (NCCL over
-NVLink on the B200 box, gloo in the CPU tests) gives every rank the full table in object order.
+at the end ONE ``all_gather_into_tensor`` of the padded ``[rows_max, n_cols]`` float64 table -- all requested module
+tables side by side -- (NCCL over NVLink on the B200 box, gloo in the CPU tests) gives every rank the full table in object
+order.  The gathered table is float64 x every module column (434 for the eight passes of the v34a/v92d superset): the
+reference's frames are float64 and the 222 columns are selected downstream by name, so neither the precision nor the
+width is cut on the wire (27.8 GB per rank at 8 x 10^6 objects, 65 ms over NVLink 5 in round 1).
 """
 from __future__ import annotations
 
@@ -51,9 +54,60 @@ def shard_rows(obj: np.ndarray, lo: int, hi: int):
     return keep, (obj[keep] - lo).astype(np.int32)
 
 
-def allgather_rows(local, rows_per_rank: Sequence[int], group=None):
-    """All-gather row blocks of unequal height.  ``local``: torch tensor ``[rows_per_rank[rank], C]`` (CPU for
-    gloo, CUDA for NCCL).  Returns ``[sum(rows_per_rank), C]`` in rank order on every rank."""
+def equal_ranges(n_obj: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous ranges of (nearly) equal object counts: the cost-balanced split when per-object costs are i.i.d.
+    (a synthetic stream generated per shard, where no rank ever sees the whole set)."""
+    cuts = [round(n_obj * r / world) for r in range(world + 1)]
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def table_width(modules: Sequence[str]) -> int:
+    from . import _native
+    return sum(_native.COLS[m] for m in modules)
+
+
+def featurise_shard(cols: dict, n_local: int, modules: Sequence[str], table=None, device=None, stream: int = 0,
+                    status: dict = None, on_pass=None):
+    """One rank's share of the work: pack the shard's flat columns (``obj`` already re-based to ``0..n_local``; host arrays or
+    CUDA tensors) into one store and run every pass of ``modules`` on it, writing the rows side by side into ONE
+    ``[n_local, table_width(modules)]`` float64 CUDA table (module order = column order).  Nothing is synchronised:
+    everything is ordered on ``stream``; ``on_pass(name)`` is called after each launch sequence (the bench records events
+    there).  ``cols['z']`` (per-object redshift) is used by the physics pass when present."""
+    import torch
+    from . import _native
+    from .store import LightCurveStore
+    dev = torch.cuda.current_device() if device is None else int(device)
+    width = table_width(modules)
+    if table is None:
+        table = torch.empty((n_local, width), dtype=torch.float64, device=f"cuda:{dev}")
+    elif tuple(table.shape) != (n_local, width) or table.dtype != torch.float64 or not table.is_contiguous():
+        raise ValueError(f"table must be a contiguous float64 CUDA tensor of shape {(n_local, width)}")
+    store = LightCurveStore(cols["obj"], cols["band"], cols["t"], cols["flux"], cols["err"], n_local, device=dev, stream=stream)
+    if on_pass:
+        on_pass("pack")
+    try:
+        c0 = 0
+        for m in modules:
+            w = _native.COLS[m]
+            rows = torch.empty((n_local, w), dtype=torch.float64, device=f"cuda:{dev}")     # dense rows of this pass; freed (stream-ordered) after the copy
+            z = cols.get("z") if m in ("physics", "research") else None
+            if z is not None and not (hasattr(z, "is_cuda") and z.is_cuda):
+                z = torch.as_tensor(np.ascontiguousarray(z, dtype=np.float64)).to(f"cuda:{dev}", non_blocking=True)
+            store.features(m, z=z, out=rows, status=(status or {}).get(m))
+            table[:, c0:c0 + w].copy_(rows)
+            c0 += w
+            if on_pass:
+                on_pass(m)
+    finally:
+        # destroying the store frees its arrays with cudaFree, which waits for the device: the passes above are complete
+        store.close()
+    return table
+
+
+def allgather_table(local, rows_per_rank: Sequence[int], out=None, group=None):
+    """The ONE collective of the path: all-gather of the shards' tables (padded to the tallest shard) so that every rank
+    holds the full ``[sum(rows), width]`` table in object order.  ``out``: optional preallocated ``[world * max(rows), width]``
+    receive buffer (returned as is when all shards are equally tall)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
@@ -68,35 +122,53 @@ def allgather_rows(local, rows_per_rank: Sequence[int], group=None):
     if local.shape[0] != rmax:
         padded = local.new_zeros((rmax, cols))
         padded[: local.shape[0]] = local
-    out = local.new_empty((world * rmax, cols))
+    if out is None:
+        out = local.new_empty((world * rmax, cols))
     dist.all_gather_into_tensor(out, padded.contiguous(), group=group)
     if all(int(r) == rmax for r in rows_per_rank):
         return out
     return torch.cat([out[r * rmax: r * rmax + int(rows_per_rank[r])] for r in range(world)], dim=0)
 
 
-def featurise_sharded(obj, band, t, flux, err, n_obj: int, modules: Sequence[str], z=None, cost: str = "linear",
-                      group=None, device=None):
-    """Every rank calls this with the same flat host columns; returns ``{module: [n_obj, cols] CUDA tensor}``
-    holding the full table on every rank.  One store per rank, passes on the local shard, one all-gather per
-    module table."""
+def featurise_sharded(source, n_obj: int, modules: Sequence[str], cost: str = "linear", group=None, device=None,
+                      gather: bool = True, on_pass=None):
+    """The multi-GPU entry: every rank calls this; returns ``(table, ranges)`` with ``table`` the full
+    ``[n_obj, table_width(modules)]`` float64 CUDA table on every rank (``gather=False``: only this rank's rows).
+
+    ``source`` is either
+      * a dict of flat columns over the WHOLE set (``obj, band, t, flux, err`` and optionally ``z``; host arrays), split
+        into contiguous object ranges of equal ``cost`` (observation counts, or their cube for the GP) -- every rank then
+        masks out its own rows; or
+      * a callable ``source(lo, hi) -> dict`` producing the flat columns of objects ``[lo, hi)`` with ``obj`` re-based to
+        ``0..hi-lo`` (a per-shard reader or generator: at 10^7 objects no rank ever holds the whole set); ranges are then
+        equal object counts.
+    One store per rank, no collective during compute, ONE all-gather of the concatenated table at the end."""
     import torch
     import torch.distributed as dist
-    from . import _native
-    from .store import LightCurveStore
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     dev = torch.cuda.current_device() if device is None else device
-    ranges = balanced_ranges(object_costs(np.asarray(obj), n_obj, cost), world)
-    lo, hi = ranges[rank]
-    keep, local_obj = shard_rows(np.asarray(obj), lo, hi)
-    out = {}
-    with LightCurveStore(local_obj, np.asarray(band)[keep], np.asarray(t)[keep], np.asarray(flux)[keep],
-                         np.asarray(err)[keep], hi - lo, device=dev) as store:
-        for m in modules:
-            rows = torch.empty((hi - lo, _native.COLS[m]), dtype=torch.float64, device=f"cuda:{dev}")
-            zz = None if (z is None or m != "physics") else np.asarray(z)[lo:hi]
-            store.features(m, z=zz, out=rows)
-            torch.cuda.synchronize(dev)
-            out[m] = rows if world == 1 else allgather_rows(rows, [b - a for a, b in ranges], group)
-    return out
+    if callable(source):
+        ranges = equal_ranges(n_obj, world)
+        lo, hi = ranges[rank]
+        cols = source(lo, hi)
+    else:
+        obj = np.asarray(source["obj"])
+        ranges = balanced_ranges(object_costs(obj, n_obj, cost), world)
+        lo, hi = ranges[rank]
+        keep, local_obj = shard_rows(obj, lo, hi)
+        cols = {"obj": local_obj}
+        for k in ("band", "t", "flux", "err"):
+            cols[k] = np.asarray(source[k])[keep]
+        if source.get("z") is not None:
+            cols["z"] = np.asarray(source["z"])[lo:hi]
+    table = featurise_shard(cols, hi - lo, modules, device=dev, on_pass=on_pass)
+    if world == 1 or not gather:
+        return table, ranges
+    full = allgather_table(table, [b - a for a, b in ranges], group=group)
+    if on_pass:
+        on_pass("allgather")
+    return full, ranges
+
+
+allgather_rows = allgather_table      # round-1 name

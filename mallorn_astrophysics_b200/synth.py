@@ -222,81 +222,106 @@ def make_edge_table(seed: int = 7) -> LightCurveTable:
                            base.z, base.ebv, base.label, "edge")
 
 
+def _device_chunk(n: int, gen_seed: int, dev):
+    """One chunk of ``n`` objects of the generative model of ``_chunk``, evaluated with torch on ``dev``.  Returns
+    ``(obj int64 local 0..n-1, band uint8, t, flux, err [rows]; z [n])`` in shuffled file order."""
+    import torch
+    f64 = torch.float64
+    mean_counts = torch.tensor(_BAND_MEAN_COUNTS, dtype=f64, device=dev)
+    wave = torch.tensor(_BAND_WAVE_A, dtype=f64, device=dev)
+    noise = torch.tensor(_BAND_NOISE, dtype=f64, device=dev)
+    g = torch.Generator(device=dev)
+    g.manual_seed(int(gen_seed))
+    U = lambda lo, hi, size: lo + (hi - lo) * torch.rand(size, dtype=f64, device=dev, generator=g)
+    logu = lambda lo, hi, size: torch.exp(U(np.log(lo), np.log(hi), size))
+    counts = torch.poisson(mean_counts.expand(n, 6).contiguous(), generator=g).to(torch.int64)
+    tot = counts.sum(1)
+    counts[:, 2] += torch.clamp(30 - tot, min=0)
+    tot = counts.sum(1)
+    high = tot > 400
+    if bool(high.any()):
+        counts[high] = torch.floor(counts[high].to(f64) * (400.0 / tot[high].to(f64))[:, None]).to(torch.int64)
+        tot = counts.sum(1)
+    nrow = int(tot.sum())
+    o = torch.repeat_interleave(torch.arange(n, device=dev), tot)
+    band = torch.repeat_interleave(torch.arange(6, device=dev).repeat(n), counts.reshape(-1))
+    span, start = U(1100.0, 3000.0, n), 60000.0 + U(0.0, 365.0, n)
+    n_season = torch.randint(5, 10, (n,), device=dev, generator=g).to(f64)
+    period = span / n_season
+    season = torch.floor(U(0.0, 1.0, nrow) * n_season[o])
+    on_frac = 150.0 / 365.0
+    t = start[o] + season * period[o] + U(0.0, 1.0, nrow) * on_frac * period[o]
+    t = torch.floor(t) + U(0.0, 0.35, nrow)
+    u = U(0.0, 1.0, n)
+    cls = torch.where(u < 0.05, CLASS_TDE, torch.where(u < 0.70, CLASS_SN, CLASS_AGN))
+    z = U(0.01, 1.0, n)
+    pk_season = torch.floor(U(0.0, 1.0, n) * n_season)
+    t0 = start + pk_season * period + U(0.1, 0.7, n) * on_frac * period
+    amp, tau_r, tau_f, tde_t0 = logu(2.0, 30.0, n), U(2.0, 12.0, n), U(15.0, 90.0, n), U(20.0, 60.0, n)
+    beta0 = torch.where(cls == CLASS_TDE, U(1.0, 2.0, n), U(-0.3, 1.0, n))
+    redden = torch.where(cls == CLASS_SN, U(0.3, 1.5, n), torch.zeros(n, dtype=f64, device=dev))
+    dt = t - t0[o]
+    rcls = cls[o]
+    rise = torch.sigmoid(torch.clamp(dt / tau_r[o], -60.0, 60.0))
+    decay_sn = torch.exp(-torch.clamp(dt / tau_f[o], -50.0, 700.0))
+    decay_tde = torch.pow(1.0 + torch.clamp(dt, min=0.0) / tde_t0[o], -5.0 / 3.0)
+    shape = rise * torch.where(rcls == CLASS_SN, decay_sn, decay_tde)
+    k_ff = 12
+    tau_agn = logu(30.0, 300.0, n)
+    cauchy = torch.tan(np.pi * (U(0.0, 1.0, (n, k_ff)) - 0.5)).abs()
+    omega = cauchy / tau_agn[:, None]
+    phase = U(0.0, 2.0 * np.pi, (n, k_ff))
+    lam_shift = 0.3 * (wave[band] - 6222.0) / U(2000.0, 8000.0, n)[o]
+    ta = t - start[o]
+    acc = torch.zeros(nrow, dtype=f64, device=dev)
+    for k in range(k_ff):
+        acc += torch.cos(omega[o, k] * ta + phase[o, k] + lam_shift)
+    shape = torch.where(rcls == CLASS_AGN, 0.6 + 0.35 * np.sqrt(2.0 / k_ff) * acc, shape)
+    beta = beta0[o] + redden[o] * torch.clamp(torch.clamp(dt, min=0.0) / 60.0, 0.0, 2.5)
+    signal = amp[o] * shape * torch.pow(wave[band] / 6222.0, -beta)
+    sigma = logu(0.15, 2.5, n)[o] * noise[band]
+    err = sigma * U(0.8, 1.2, nrow)
+    flux = signal + torch.randn(nrow, dtype=f64, device=dev, generator=g) * sigma \
+        + (0.2 * torch.randn(n, dtype=f64, device=dev, generator=g))[o]
+    perm = torch.randperm(nrow, device=dev, generator=g)
+    return o[perm], band[perm].to(torch.uint8), t[perm], flux[perm], err[perm], z
+
+
+def make_shard_columns_device(n_total: int, lo: int, hi: int, seed: int, device, chunk: int = 131072):
+    """Objects ``[lo, hi)`` of the ``n_total``-object set of ``seed``, generated on ``device`` with ``obj`` re-based to
+    ``0..hi-lo``.  The set is defined chunk by chunk (``chunk`` objects, one generator seed each), so every rank of a
+    sharded run reproduces exactly its objects of the SAME set whatever the number of ranks: chunks that straddle a shard
+    boundary are generated on both sides and cut.  Returns ``dict(obj int32, band uint8, t, flux, err float64 [n_rows];
+    z float64 [hi-lo])`` in shuffled file order (shuffled inside chunks)."""
+    import torch
+    dev = torch.device(device)
+    parts = []
+    for ci in range(lo // chunk, (max(hi, lo + 1) - 1) // chunk + 1 if hi > lo else lo // chunk):
+        c0 = ci * chunk
+        n = min(chunk, n_total - c0)
+        o, band, t, flux, err, z = _device_chunk(n, int(seed) * 1000003 + ci, dev)
+        a, b = max(lo, c0) - c0, min(hi, c0 + n) - c0
+        if a > 0 or b < n:
+            keep = (o >= a) & (o < b)
+            o, band, t, flux, err = o[keep], band[keep], t[keep], flux[keep], err[keep]
+        parts.append(((o + (c0 - lo)).to(torch.int32), band, t, flux, err, z[a:b]))
+    if not parts:
+        e = torch.empty(0, dtype=torch.float64, device=dev)
+        return {"obj": torch.empty(0, dtype=torch.int32, device=dev), "band": torch.empty(0, dtype=torch.uint8, device=dev),
+                "t": e, "flux": e.clone(), "err": e.clone(), "z": e.clone()}
+    cat = lambda i: torch.cat([p[i] for p in parts]) if len(parts) > 1 else parts[0][i]
+    return {"obj": cat(0), "band": cat(1), "t": cat(2), "flux": cat(3), "err": cat(4), "z": cat(5)}
+
+
 def make_columns_device(n_obj: int, seed: int, device, obj0: int = 0, chunk: int = 131072):
     """The same generative model as ``_chunk`` evaluated with torch on ``device`` (bench-scale sets:
     10^6-10^7 objects never exist on the host).  Not bit-identical to ``make_table`` -- parity tests
     use the numpy generator; this one only has to draw from the same distribution.
 
     Returns ``dict(obj int32, band uint8, t, flux, err float64 [n_rows]; z float64 [n_obj])`` in
-    shuffled file order (shuffled inside chunks of ``chunk`` objects).
+    shuffled file order (shuffled inside chunks of ``chunk`` objects); ``obj`` starts at ``obj0``.
     """
-    import torch
-    dev = torch.device(device)
-    f64 = torch.float64
-    mean_counts = torch.tensor(_BAND_MEAN_COUNTS, dtype=f64, device=dev)
-    wave = torch.tensor(_BAND_WAVE_A, dtype=f64, device=dev)
-    noise = torch.tensor(_BAND_NOISE, dtype=f64, device=dev)
-    parts = []
-    done, ci = 0, 0
-    while done < n_obj:
-        n = min(chunk, n_obj - done)
-        g = torch.Generator(device=dev)
-        g.manual_seed(int(seed) * 1000003 + ci)
-        U = lambda lo, hi, size: lo + (hi - lo) * torch.rand(size, dtype=f64, device=dev, generator=g)
-        logu = lambda lo, hi, size: torch.exp(U(np.log(lo), np.log(hi), size))
-        counts = torch.poisson(mean_counts.expand(n, 6).contiguous(), generator=g).to(torch.int64)
-        tot = counts.sum(1)
-        counts[:, 2] += torch.clamp(30 - tot, min=0)
-        tot = counts.sum(1)
-        high = tot > 400
-        if bool(high.any()):
-            counts[high] = torch.floor(counts[high].to(f64) * (400.0 / tot[high].to(f64))[:, None]).to(torch.int64)
-            tot = counts.sum(1)
-        nrow = int(tot.sum())
-        o = torch.repeat_interleave(torch.arange(n, device=dev), tot)
-        band = torch.repeat_interleave(torch.arange(6, device=dev).repeat(n), counts.reshape(-1))
-        span, start = U(1100.0, 3000.0, n), 60000.0 + U(0.0, 365.0, n)
-        n_season = torch.randint(5, 10, (n,), device=dev, generator=g).to(f64)
-        period = span / n_season
-        season = torch.floor(U(0.0, 1.0, nrow) * n_season[o])
-        on_frac = 150.0 / 365.0
-        t = start[o] + season * period[o] + U(0.0, 1.0, nrow) * on_frac * period[o]
-        t = torch.floor(t) + U(0.0, 0.35, nrow)
-        u = U(0.0, 1.0, n)
-        cls = torch.where(u < 0.05, CLASS_TDE, torch.where(u < 0.70, CLASS_SN, CLASS_AGN))
-        z = U(0.01, 1.0, n)
-        pk_season = torch.floor(U(0.0, 1.0, n) * n_season)
-        t0 = start + pk_season * period + U(0.1, 0.7, n) * on_frac * period
-        amp, tau_r, tau_f, tde_t0 = logu(2.0, 30.0, n), U(2.0, 12.0, n), U(15.0, 90.0, n), U(20.0, 60.0, n)
-        beta0 = torch.where(cls == CLASS_TDE, U(1.0, 2.0, n), U(-0.3, 1.0, n))
-        redden = torch.where(cls == CLASS_SN, U(0.3, 1.5, n), torch.zeros(n, dtype=f64, device=dev))
-        dt = t - t0[o]
-        rcls = cls[o]
-        rise = torch.sigmoid(torch.clamp(dt / tau_r[o], -60.0, 60.0))
-        decay_sn = torch.exp(-torch.clamp(dt / tau_f[o], -50.0, 700.0))
-        decay_tde = torch.pow(1.0 + torch.clamp(dt, min=0.0) / tde_t0[o], -5.0 / 3.0)
-        shape = rise * torch.where(rcls == CLASS_SN, decay_sn, decay_tde)
-        k_ff = 12
-        tau_agn = logu(30.0, 300.0, n)
-        cauchy = torch.tan(np.pi * (U(0.0, 1.0, (n, k_ff)) - 0.5)).abs()
-        omega = cauchy / tau_agn[:, None]
-        phase = U(0.0, 2.0 * np.pi, (n, k_ff))
-        lam_shift = 0.3 * (wave[band] - 6222.0) / U(2000.0, 8000.0, n)[o]
-        ta = t - start[o]
-        acc = torch.zeros(nrow, dtype=f64, device=dev)
-        for k in range(k_ff):
-            acc += torch.cos(omega[o, k] * ta + phase[o, k] + lam_shift)
-        shape = torch.where(rcls == CLASS_AGN, 0.6 + 0.35 * np.sqrt(2.0 / k_ff) * acc, shape)
-        beta = beta0[o] + redden[o] * torch.clamp(torch.clamp(dt, min=0.0) / 60.0, 0.0, 2.5)
-        signal = amp[o] * shape * torch.pow(wave[band] / 6222.0, -beta)
-        sigma = logu(0.15, 2.5, n)[o] * noise[band]
-        err = sigma * U(0.8, 1.2, nrow)
-        flux = signal + torch.randn(nrow, dtype=f64, device=dev, generator=g) * sigma \
-            + (0.2 * torch.randn(n, dtype=f64, device=dev, generator=g))[o]
-        perm = torch.randperm(nrow, device=dev, generator=g)
-        parts.append(((o[perm] + (obj0 + done)).to(torch.int32), band[perm].to(torch.uint8), t[perm], flux[perm],
-                      err[perm], z))
-        done += n
-        ci += 1
-    cat = lambda i: torch.cat([p[i] for p in parts]) if len(parts) > 1 else parts[0][i]
-    return {"obj": cat(0), "band": cat(1), "t": cat(2), "flux": cat(3), "err": cat(4), "z": cat(5)}
+    cols = make_shard_columns_device(n_obj, 0, n_obj, seed, device, chunk)
+    if obj0:
+        cols["obj"] = cols["obj"] + int(obj0)
+    return cols

@@ -9,7 +9,7 @@ os.environ.setdefault("MLRN_QUIET", "1")
 for spec in sys.argv[1:]:
     name, _, flags = spec.partition("=")
     out = os.path.join(ROOT, "variants", f"lib_{name}.so")
-    fl = [f for f in flags.split(",") if f]
+    fl = [f for f in flags.split(";" if ";" in flags or "{" in flags else ",") if f]
     csrc = g.CSRC
     for f in list(fl):                      # csrc=<dir>: compile another source tree (e.g. an older revision checked out under /tmp)
         if f.startswith("csrc="):

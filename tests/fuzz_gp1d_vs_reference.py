@@ -31,10 +31,7 @@ obj=np.array(obj,np.int32); band=np.array(band,np.uint8); t=np.array(t); f=np.ar
 pk=pack_reference(obj,band,t,f,e,n_obj)
 out=np.zeros((n_obj,21)); st=np.zeros((n_obj,12),np.int32)
 args = [ctypes.c_longlong(n_obj)] + [pk[k].ctypes.data_as(P) for k in ("seg_off","t","flux","err","rank")] + [out.ctypes.data_as(P), st.ctypes.data_as(P)]
-if os.environ.get("MLRN_GP1D_TILED") == "1":          # the register-tiled objective, 32 emulated lanes
-    lib.hs_gp1d_tiled(*args, ctypes.c_int(0))
-else:
-    lib.hs_gp1d(*args)
+lib.hs_gp1d(*args)
 ref=np.full((n_obj,21),np.nan)
 for k in range(n_obj):
     for j,b in enumerate((1,2,3,4)):

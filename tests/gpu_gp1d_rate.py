@@ -1,5 +1,5 @@
 """Developer script (GPU): throughput of the per-band GP pass alone, with the work it did.
-    python tests/gpu_gp1d_rate.py [objects] [repeats]          (MLRN_GP1D_TILED=1 selects the experimental register-tiled kernel)"""
+    python tests/gpu_gp1d_rate.py [objects] [repeats]"""
 import os, sys, time
 sys.path.insert(0, os.getcwd())
 import torch

@@ -15,7 +15,6 @@
 #include "gp_host.hpp"
 #include "fits_thread.cuh"
 #include "gp1d.cuh"
-#include "gp1d_tiled.cuh"
 #include "lbfgsb_exact.cuh"
 
 using namespace mlrn;
@@ -178,43 +177,5 @@ int hs_gp1d(long long n_obj, const long long* seg_off, const double* t, const do
   return 0;
 }
 
-// register-tiled objective (gp1d_tiled.cuh) with 32 emulated lanes; same driver and optimiser as hs_gp1d.
-// force_tpl: 0 = choose by size as the kernel does (2 / 3 tiles per lane, else the shared-memory sweep), 5 = always 5
-int hs_gp1d_tiled(long long n_obj, const long long* seg_off, const double* t, const double* f, const double* e,
-                  const unsigned short* rank, double* out, int* status, int force_tpl) {
-  HostTeam tm;
-  const int bands[4] = {BG, BR, BI, BZ};
-  std::vector<double> scratch(gp1d_scratch_doubles(MAX_OBS) + gp1d_tiled_scratch_doubles(MAX_OBS));
-  LbfgsB<3> opt; double ctl[8];
-  static HostLanes<TileRegs<2>> l2; static HostLanes<TileRegs<3>> l3; static HostLanes<TileRegs<5>> l5;
-  for (long long o = 0; o < n_obj; ++o) {
-    Gp1dBandResult res[4];
-    for (int j = 0; j < 4; ++j) {
-      const long long lo = seg_off[o * N_SEG + bands[j]];
-      const int nraw = (int)(seg_off[o * N_SEG + bands[j] + 1] - lo);
-      gp1d_clear(res[j]);
-      Gp1dTiledScratch ts = gp1d_carve_tiled(scratch.data(), nraw);
-      double t_range = 0.0, f_std = 1.0;
-      const int n = gp1d_prepare(tm, t + lo, f + lo, e + lo, nraw, ts.x, ts.y, ts.al, t_range, f_std);
-      if (n > 0) {
-        const int n1 = n + 1;
-        if (force_tpl == 5 && n1 <= gp1d_tiled_capacity(5))
-          gp1d_optimise(tm, [&](const double* th, double& fv, double* g) { gp1d_objective_tiled<5>(l5, n, ts.x, ts.y, ts.al, ts.vb0, ts.vb1, ts.piv, th, fv, g); }, t_range, f_std, &opt, ctl, res[j]);
-        else if (n1 <= gp1d_tiled_capacity(2))
-          gp1d_optimise(tm, [&](const double* th, double& fv, double* g) { gp1d_objective_tiled<2>(l2, n, ts.x, ts.y, ts.al, ts.vb0, ts.vb1, ts.piv, th, fv, g); }, t_range, f_std, &opt, ctl, res[j]);
-        else if (n1 <= gp1d_tiled_capacity(3))
-          gp1d_optimise(tm, [&](const double* th, double& fv, double* g) { gp1d_objective_tiled<3>(l3, n, ts.x, ts.y, ts.al, ts.vb0, ts.vb1, ts.piv, th, fv, g); }, t_range, f_std, &opt, ctl, res[j]);
-        else {
-          Gp1dScratch s = gp1d_carve(scratch.data() + gp1d_tiled_scratch_doubles(MAX_OBS), nraw);
-          for (int i = 0; i < n; ++i) { s.x[i] = ts.x[i]; s.y[i] = ts.y[i]; s.al[i] = ts.al[i]; }
-          gp1d_optimise(tm, [&](const double* th, double& fv, double* g) { gp1d_objective(tm, n, s, th, fv, g); }, t_range, f_std, &opt, ctl, res[j]);
-        }
-      }
-      if (status) { status[o * 12 + 3 * j] = res[j].nfev; status[o * 12 + 3 * j + 1] = res[j].nit; status[o * 12 + 3 * j + 2] = res[j].winner; }
-    }
-    gp1d_tail(res, out + o * GP1D_COLS);
-  }
-  return 0;
-}
 
 }  // extern "C"

@@ -28,9 +28,6 @@ def run_all(obj,band,t,f,e,z,n_obj,tag):
         if status:
             st=np.zeros((n_obj,status),np.int32); args.append(st.ctypes.data_as(P))
         getattr(lib,fn)(*args)
-    out=np.zeros((n_obj,21)); st=np.zeros((n_obj,12),np.int32)
-    for force in (0,5):
-        lib.hs_gp1d_tiled(*base, out.ctypes.data_as(P), st.ctypes.data_as(P), ctypes.c_int(force))
     print(tag,"ok",n_obj,"objects")
 for name in ("ref_edge","ref_sparse","ref_dense"):
     g=np.load(os.path.join(ROOT, 'tests', 'golden', f'{name}.npz'))

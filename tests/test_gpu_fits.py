@@ -35,11 +35,32 @@ def test_bazin_matches_reference_golden(golden, fixture):
     c = classify_bazin(got, want)
     print(fixture, c)
     assert c["fits"] > 50
-    assert c["match"] >= 0.60 * c["fits"], c
+    # per fixture (100-760 fits each, so a few points of sampling noise); the aggregate rule is in the next test
+    assert c["match"] >= 0.62 * c["fits"], c
+    assert c["worse"] <= 0.06 * c["fits"] + 1, c
     assert c["match"] + c["no_worse"] >= 0.93 * c["fits"], c
     assert c["nan_diff"] <= 0.02 * c["fits"] + 1, c
     # bands the reference never fits (n < 5) are NaN on both sides and flagged FIT_SKIPPED
     assert (status[..., 1][status[..., 0] == -200] == 0).all()
+
+
+def test_bazin_classes_over_all_reference_fits(golden):
+    """The measured level, not a loose floor: over the 2,047 fits the unmodified reference attempted on the four fixtures the
+    B200 lands within rtol 1e-3 on 72 %, on a different point that is no worse on 25 %, on a worse one on 3 %
+    (DESIGN.md section 5).  That split is the reference's OWN reproducibility under a 1-ulp change of exp()
+    (70.4 / 27.1 / 2.4, tests/test_fit_ceiling.py), so the assertions sit just under it: a regression of a few points fails."""
+    tot = {"fits": 0, "match": 0, "no_worse": 0, "worse": 0, "nan_diff": 0}
+    for fixture in ("ref_sparse", "ref_dense", "ref_edge", "ref_c1_256"):
+        with _store(golden[fixture]) as s:
+            got = s.features("bazin")
+        c = classify_bazin(*_golden(golden, fixture, "bazin", got))
+        for k in tot:
+            tot[k] += c[k]
+    print(tot)
+    assert tot["fits"] > 2000
+    assert tot["match"] >= 0.68 * tot["fits"], tot
+    assert tot["worse"] <= 0.04 * tot["fits"], tot
+    assert tot["nan_diff"] <= 0.01 * tot["fits"], tot
 
 
 @pytest.mark.parametrize("fixture", ["ref_sparse", "ref_dense", "ref_edge", "ref_c1_256"])
@@ -50,7 +71,8 @@ def test_powerlaw_matches_reference_golden(golden, fixture):
     c = classify_r2(got, want)
     print(fixture, c)
     assert c["match"] >= 0.97 * c["fits"], c
-    assert c["worse"] <= 0.005 * c["fits"] + 1 and c["worst"] < 0.15, c        # a different local minimum in < 0.5 % of fits
+    # a different local minimum in < 0.5 % of fits; the largest R^2 deficit seen on any set so far is 0.133
+    assert c["worse"] <= 0.005 * c["fits"] + 1 and c["worst"] < 0.15, c
     assert c["nan_diff"] <= 0.005 * c["fits"] + 1, c
 
 
@@ -82,5 +104,6 @@ def test_fits_match_oracle_at_scale():
         _, wp = run_table("powerlaw", table)
     cb, cp = classify_bazin(gb[present], wb), classify_r2(gp[present], wp)
     print(cb, cp)
-    assert cb["match"] >= 0.60 * cb["fits"] and cb["match"] + cb["no_worse"] >= 0.93 * cb["fits"], cb
-    assert cp["match"] >= 0.97 * cp["fits"], cp
+    assert cb["match"] >= 0.62 * cb["fits"] and cb["match"] + cb["no_worse"] >= 0.93 * cb["fits"], cb
+    assert cb["worse"] <= 0.05 * cb["fits"] and cb["nan_diff"] <= 0.01 * cb["fits"] + 1, cb
+    assert cp["match"] >= 0.97 * cp["fits"] and cp["worst"] < 0.15, cp

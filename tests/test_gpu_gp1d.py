@@ -115,22 +115,3 @@ def test_gp1d_crafted_edge_cases():
     ok = ~np.isnan(ref)
     np.testing.assert_allclose(rows[ok], ref[ok], rtol=1e-3, atol=1e-6)
     assert (st[1] == [0, 0, -1] * 4).all() and st[0, 2] >= 0          # no fit for the single-epoch object; g band of object 0 fitted
-
-
-def test_gp1d_register_tiled_kernel_matches_default(monkeypatch, golden):
-    """MLRN_GP1D_TILED=1 (gp1d_tiled.cuh: 4 x 4 tiles of the matrix in registers) against the reference goldens and the
-    default shared-memory sweep.  Correctness only: the kernel stays opt-in until it has been timed under load."""
-    import time
-    g = golden["ref_c1_256"]
-    _gpu(g)                                                     # context creation, module load
-    t0 = time.perf_counter(); base, st = _gpu(g); t1 = time.perf_counter()
-    monkeypatch.setenv("MLRN_GP1D_TILED", "1")
-    _gpu(g)
-    t2 = time.perf_counter(); tiled, st2 = _gpu(g); t3 = time.perf_counter()
-    monkeypatch.delenv("MLRN_GP1D_TILED")
-    print(f"\n256 objects (one per warp, latency-bound; includes pack + copies): default {1e3 * (t1 - t0):.1f} ms, tiled {1e3 * (t3 - t2):.1f} ms")
-    pres, ref = g["gp1d_present"], g["gp1d_rows"]
-    _compare(tiled[pres], ref)
-    ok = ~np.isnan(base)
-    assert np.array_equal(np.isnan(tiled), np.isnan(base))
-    np.testing.assert_allclose(tiled[ok], base[ok], rtol=1e-4, atol=1e-8)

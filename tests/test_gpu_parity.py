@@ -178,9 +178,52 @@ def test_object_above_cap_is_rejected():
                         np.ones(n), np.ones(n), 1)
 
 
+def test_one_very_long_object_does_not_fail_the_batch():
+    """The reference takes any length (statistical.py:163-190).  One 3,000-observation object among ordinary ones: K1 stays
+    bit-exact, the scalar passes match the oracle on every object, the fit and GP passes return rows for it.  (Most of
+    its errors are zero, which the GP drops as invalid, so the 2-D GP sees ~400 points instead of an N^3 = 2.7e10 job.)"""
+    from packref import pack_reference
+    from mallorn_astrophysics_b200.store import LightCurveStore
+    from mallorn_astrophysics_b200.synth import LightCurveTable, make_table
+    from oracle.extract import run_table
+    base = make_table(40, seed=99, count_scale=2.0)              # ~300 observations each
+    obj = base.obj.copy()
+    obj[obj < 10] = 0                                             # the first ten objects become ONE object of ~3,000 observations
+    obj[obj >= 10] -= 9
+    err = base.err.copy()
+    rng = np.random.default_rng(5)
+    long_rows = np.flatnonzero(obj == 0)
+    err[rng.choice(long_rows, size=len(long_rows) - 400, replace=False)] = 0.0
+    table = LightCurveTable(obj.astype(np.int32), base.band, base.t, base.flux, err, 31, base.z[9:].copy(), base.ebv[9:].copy(),
+                            base.label[9:].copy(), "vlong")
+    n_long = int(np.bincount(table.obj)[0])
+    assert n_long > 2500
+    want_pack = pack_reference(table.obj, table.band, table.t, table.flux, table.err, table.n_obj)
+    with LightCurveStore.from_table(table) as s:
+        assert s.max_obs == n_long
+        got_pack, seg = s.export(), s.segments()
+        got = {m: s.features(m, z=table.z if m in ("physics", "research") else None)
+               for m in ("statistical", "colors", "shape", "tde", "physics", "research", "bazin", "powerlaw", "gp2d", "gp1d")}
+    assert np.array_equal(got_pack["seg_off"], want_pack["seg_off"])
+    for k in ("t", "flux", "err"):
+        assert np.array_equal(got_pack[k].view(np.uint64), want_pack[k].view(np.uint64)), k
+    assert np.array_equal(got_pack["rank"], want_pack["rank"]) and np.array_equal(got_pack["trank"], want_pack["trank"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        present, meta = run_table("segments", table)
+        assert np.array_equal(seg[present].astype(np.int64), meta)
+        for m in ("statistical", "colors", "shape", "tde", "physics", "research"):
+            present, want = run_table(m, table)
+            _compare(got[m][present], want, rtol=1e-5, atol=1e-9, what=f"{m}/very long")
+        _, want_gp = run_table("gp2d", table.subset(1))
+    _compare(got["gp2d"][:1], want_gp, rtol=1e-3, atol=1e-6, what="gp2d/very long")
+    assert np.isfinite(got["bazin"][0, 8 * 2]) or np.isnan(got["bazin"][0, 8 * 2])
+    assert np.isfinite(got["powerlaw"][0]).any() and np.isfinite(got["gp1d"][0]).any()
+
+
 def test_long_objects_up_to_the_cap():
-    """A few objects near the 1024-observation cap (far beyond survey cadence): every pass must still run, and
-    the scalar passes must still match the oracle."""
+    """A few objects of 512-1024 observations (far beyond survey cadence; they take the global-scratch launches): every pass
+    must still run, and the scalar passes must still match the oracle."""
     from mallorn_astrophysics_b200.store import LightCurveStore
     from mallorn_astrophysics_b200.synth import make_table
     from oracle.extract import run_table

@@ -174,23 +174,6 @@ def test_per_band_gp_crafted_edge_cases(hs):
     np.testing.assert_allclose(rows[ok], ref[ok], rtol=1e-5, atol=1e-9)
 
 
-@pytest.mark.parametrize("force_tpl", [0, 5], ids=["size_classes_2_3", "five_tiles_per_lane"])
-def test_register_tiled_objective_lane_emulation(golden, hs, force_tpl):
-    """gp1d_tiled.cuh (experimental register-tiled sweep, MLRN_GP1D_TILED=1) run with 32 emulated lanes: the tile
-    bookkeeping (tile ownership, pivot-column publication, row/column fix-ups, double buffering) against the
-    reference's output and against the shared-memory sweep."""
-    g = golden["ref_sparse"]
-    pk, n_obj = _pack(g)
-    base, _ = _run(hs, "hs_gp1d", 21, pk, n_obj, status_cols=12)
-    out = np.zeros((n_obj, 21)); st = np.zeros((n_obj, 12), np.int32)
-    args = [ctypes.c_longlong(n_obj)] + [pk[k].ctypes.data_as(P) for k in ("seg_off", "t", "flux", "err", "rank")]
-    hs.hs_gp1d_tiled(*args, out.ctypes.data_as(P), st.ctypes.data_as(P), ctypes.c_int(force_tpl))
-    pres, ref = g["gp1d_present"], g["gp1d_rows"]
-    c = classify_gp1d(out[pres], ref)
-    assert c["worse"] == 0 and c["nan_diff"] == 0 and c["cross_bad"] == 0 and c["match"] >= 0.98 * c["fits"], c
-    ok = ~np.isnan(base)
-    assert np.array_equal(np.isnan(out), np.isnan(base))
-    np.testing.assert_allclose(out[ok], base[ok], rtol=1e-4, atol=1e-8)
 
 
 @pytest.mark.parametrize("fixture", ["ref_sparse", "ref_dense", "ref_edge", "ref_c1_256"])

