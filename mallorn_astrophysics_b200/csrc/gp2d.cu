@@ -302,22 +302,27 @@ __device__ __forceinline__ void gp_eval(const GpShared& S, double* __restrict__ 
   double* cache_s = cache;
   double* cache_e = cache + (size_t)n_tiles(T_cap) * TT;
   // ---- (a) kernel matrix, b = y - mean
-  for (int e = tid; e < nt * TT; e += GP_THREADS) {           // e = storage index: tile, then fragment order
+  // e = storage index: tile, then fragment order.  Branch-free body, two elements per trip: the sqrt and exp chains of
+  // the pair interleave (the loop is bound by FP64 latency, not by its 4 shared-memory loads).
+  auto element = [&](int e) {
     const int tl = e >> 8;
     int r, c;
     tix_decode(e & 255, r, c);
     const int gi = S.tI[tl] * TB + r, gj = S.tJ[tl] * TB + c;
-    double v;
-    if (gi >= n || gj >= n) v = (gi == gj) ? 1.0 : 0.0;
-    else {
-      const double dt = S.st[gi] - S.st[gj], dl = S.sl[gi] - S.sl[gj];
-      const double s = sqrt(3.0 * (dt * dt * kp.im0 + dl * dl * kp.im1));
-      const double ex = exp(-s);
-      cache_s[e] = s; cache_e[e] = ex;
-      v = kp.amp * (1.0 + s) * ex;
-      if (gi == gj) v += S.sn[gi];
-    }
-    S.tiles[e] = v;
+    const bool ok = gi < n && gj < n;
+    const int ia = ok ? gi : 0, ib = ok ? gj : 0;
+    const double dt = S.st[ia] - S.st[ib], dl = S.sl[ia] - S.sl[ib];
+    const double s = sqrt(3.0 * (dt * dt * kp.im0 + dl * dl * kp.im1));
+    const double ex = exp(-s);
+    double v = kp.amp * (1.0 + s) * ex;
+    if (gi == gj) v += S.sn[ia];
+    if (ok) { cache_s[e] = s; cache_e[e] = ex; }
+    S.tiles[e] = ok ? v : ((gi == gj) ? 1.0 : 0.0);
+  };
+  {
+    int e = tid;
+    for (; e + GP_THREADS < nt * TT; e += 2 * GP_THREADS) { element(e); element(e + GP_THREADS); }
+    if (e < nt * TT) element(e);
   }
   for (int i = tid; i < T * TB; i += GP_THREADS) S.sb[i] = (i < n) ? S.sy[i] - kp.mean : 0.0;
   double quad = 0.0; LogDet logdet{1.0, 0}; int fail = 0;     // accumulated by the pivot warp (uniform across its lanes)
@@ -344,7 +349,8 @@ __device__ __forceinline__ void gp_eval(const GpShared& S, double* __restrict__ 
     // Bulk tasks (rank-16 tile updates outside row/column k, then column k <- V_i Li) are dealt round-robin to the warps of
     // partitions 1..3; the tail of the last, partly filled round goes to the other warps of partition 0, which run it once
     // the next pivot tile is factored.
-    const int n_help = has_next ? ((ntask % N_BULK) < GP_WARPS / 4 - 1 ? (ntask % N_BULK) : GP_WARPS / 4 - 1) : 0;
+    // (only when that saves the bulk warps a round: otherwise the helpers' late start would be the end of the step)
+    const int n_help = (has_next && (ntask % N_BULK) >= 1 && (ntask % N_BULK) <= GP_WARPS / 4 - 1) ? (ntask % N_BULK) : 0;
     // ---- phase A: V_i = X_i Li^T for i != k, one warp per tile row.  The pivot warp takes row k+1 and then runs AHEAD
     // of the barrier (it only arrives): the update of tile (k+1, k+1), of b_{k+1} and the factorisation need V_{k+1} only.
     if (warp == PIV) {
@@ -436,7 +442,8 @@ __device__ __forceinline__ void gp_eval(const GpShared& S, double* __restrict__ 
   // ---- (c) gradient contraction: 1/2 sum (alpha_i alpha_j - Kinv_ij) dK_ij ; tiles hold -Kinv
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
   for (int i = tid; i < n; i += GP_THREADS) acc[0] += S.sb[i];
-  for (int e = tid; e < nt * TT; e += GP_THREADS) {
+  // two elements per trip with the (L2-resident) cache loads of both issued first
+  auto contract = [&](int e, double s, double ex) {
     const int tl = e >> 8;
     int r, c;
     tix_decode(e & 255, r, c);
@@ -447,10 +454,17 @@ __device__ __forceinline__ void gp_eval(const GpShared& S, double* __restrict__ 
       const double Aij = wgt * (S.sb[gi] * S.sb[gj] + S.tiles[e]);
       const double dt = S.st[gi] - S.st[gj], dl = S.sl[gi] - S.sl[gj];
       const double a0 = dt * dt * kp.im0, a1 = dl * dl * kp.im1;
-      const double s = cache_s[e], ex = cache_e[e];
       const double dk = 1.5 * kp.amp * ex;
       acc[1] += Aij * kp.amp * (1.0 + s) * ex; acc[2] += Aij * dk * a0; acc[3] += Aij * dk * a1;
     }
+  };
+  {
+    int e = tid;
+    for (; e + GP_THREADS < nt * TT; e += 2 * GP_THREADS) {
+      const double s0 = cache_s[e], x0 = cache_e[e], s1 = cache_s[e + GP_THREADS], x1 = cache_e[e + GP_THREADS];
+      contract(e, s0, x0); contract(e + GP_THREADS, s1, x1);
+    }
+    if (e < nt * TT) contract(e, cache_s[e], cache_e[e]);
   }
   GP_TICK(5);
   if (tid == PIV * 32) { S.bc[0] = quad; S.bc[1] = logdet.value(); S.bc[2] = (double)fail; }
