@@ -349,7 +349,10 @@ __device__ __forceinline__ void gp_eval(const GpShared& S, double* __restrict__ 
     // Bulk tasks (rank-16 tile updates outside row/column k, then column k <- V_i Li) are dealt round-robin to the warps of
     // partitions 1..3; the tail of the last, partly filled round goes to the other warps of partition 0, which run it once
     // the next pivot tile is factored.
-    // (only when that saves the bulk warps a round: otherwise the helpers' late start would be the end of the step)
+    // (only when that saves the bulk warps a round: otherwise the helpers' late start would be the end of the step.
+    // Also measured in round 2 and rejected: letting those warps start on bulk tasks at once -- the pivot chain slows
+    // from 4.5 k to 5.1 k cycles, 118.6 k objects/s against 121.7 k; and scaling the next step's V inside this phase behind
+    // flags instead of the scale barrier -- the scales then wait for the pivot chain, 104.9 k objects/s.)
     const int n_help = (has_next && (ntask % N_BULK) >= 1 && (ntask % N_BULK) <= GP_WARPS / 4 - 1) ? (ntask % N_BULK) : 0;
     // ---- phase A: V_i = X_i Li^T for i != k, one warp per tile row.  The pivot warp takes row k+1 and then runs AHEAD
     // of the barrier (it only arrives): the update of tile (k+1, k+1), of b_{k+1} and the factorisation need V_{k+1} only.
