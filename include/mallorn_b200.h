@@ -99,12 +99,27 @@ int mlrn_gp2d(const mlrn_store* s, double* out, int32_t* status, int out_on_devi
  * iterations over the four starts, index of the winning start (-1: band not fitted)} */
 int mlrn_gp1d(const mlrn_store* s, double* out, int32_t* status, int out_on_device, void* stream);
 
-/* EXPERIMENTAL -- "research" block of the v115c model (power-law decay quality, nuclear-position proxies, colour at
- * peak, Mexican-hat power spectra of the r band on a 1-day grid, luminosity; research_features.py:44-560).  The
- * arithmetic is verified against the reference on the CPU; the CUDA pass has not been validated on a GPU yet and is not
- * part of the default pipeline.  z: redshift per object or NULL (luminosity columns NaN, as for Z <= 0 upstream :556);
+/* K8 -- "research" block of the v115c model (power-law decay quality, nuclear-position proxies, colour at
+ * peak, Mexican-hat power spectra of the r band on a 1-day grid, luminosity; research_features.py:44-560), 40 columns,
+ * held to the reference's own frames on the B200 (tests/test_gpu_research.py).  z: redshift per object or NULL (luminosity columns NaN, as for Z <= 0 upstream :556);
  * r-band coverage beyond 8192 days leaves the six mhps_* columns NaN. */
 int mlrn_research(const mlrn_store* s, const double* z, int z_on_device, double* out, int out_on_device, void* stream);
+
+/* K9 -- feature interactions on a device-resident table.  Replaces create_physics_interactions
+ * (src/features/interactions.py:23-196): each new column is one of the seven element-wise forms below of one to three
+ * existing columns.  `table` [n_rows, ld] and `out` [n_rows, ld_out] are DEVICE pointers (row-major float64), `ops` is a
+ * HOST array of n_ops descriptors; column k of `out` receives op k.  Which interactions exist (the reference only adds
+ * those whose inputs are present) is decided by the caller from the column names (features/interactions.py). */
+enum { MLRN_IOP_MUL = 0,          /* a * b                       e.g. g_r_post_20d_x_Z           interactions.py:52 */
+       MLRN_IOP_DIV_OFFSET = 1,   /* a / (b + k)                 e.g. g_r_post_20d_div_Z (k=0.1) interactions.py:53 */
+       MLRN_IOP_DIFF_SCALED = 2,  /* (a - b) / k                 temp_drop_rate (k=50)           interactions.py:73 */
+       MLRN_IOP_CLIP_POW = 3,     /* clip(a, 0, k) ** 0.25       temp_peak_4th (k=1e5)           interactions.py:76 */
+       MLRN_IOP_SUB = 4,          /* a - b                       gr_color_accel                  interactions.py:138 */
+       MLRN_IOP_SQUARE = 5,       /* a ** 2                      r_skew_squared                  interactions.py:170 */
+       MLRN_IOP_ASYM_COLOR = 6 }; /* (a / (b + 1)) * c           g_asym_x_color                  interactions.py:116-119 */
+typedef struct mlrn_inter_op { int32_t kind, a, b, c; double k; } mlrn_inter_op;   /* b, c = -1 when unused */
+int mlrn_interactions(int device, const double* table, int64_t n_rows, int32_t ld, const mlrn_inter_op* ops, int32_t n_ops,
+                      double* out, int32_t ld_out, void* stream);
 
 #ifdef __cplusplus
 }

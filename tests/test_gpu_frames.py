@@ -132,6 +132,32 @@ def test_store_from_csv_equals_store_from_the_pandas_frame(golden, tmp_path):
             assert np.array_equal(s1.features(m), s2.features(m), equal_nan=True), m
 
 
+def test_overlapped_file_pipeline_equals_the_one_shot_path(golden, tmp_path):
+    """ingest.featurise_files (parse of file i+1 overlapped with the staging and H2D of file i, one K1 pack at the end) gives
+    the table the one-shot path (read all files, then pack) gives, bit for bit, with the same id numbering -- also when
+    an object's rows are spread over several files."""
+    import torch
+    from mallorn_astrophysics_b200 import ingest
+    from mallorn_astrophysics_b200.store import LightCurveStore
+    g = golden["ref_sparse"]
+    lc, meta, ids = _frames(g)
+    lc = lc[lc["Filter"] != "X"]
+    edges = np.linspace(0, len(lc), 4).astype(int)            # three files cutting through objects (rows are in shuffled file order)
+    paths = []
+    for i in range(3):
+        p = tmp_path / f"split_{i}.csv"
+        lc.iloc[edges[i]:edges[i + 1]].to_csv(p, index=False)
+        paths.append(p)
+    modules = ("statistical", "colors", "physics", "bazin")
+    table, got_ids, info = ingest.featurise_files(paths, modules, metadata=meta)
+    s, want_ids = LightCurveStore.from_csv(paths)
+    with s:
+        z = meta.set_index("object_id")["Z"].reindex(list(want_ids)).to_numpy()
+        want = np.concatenate([s.features(m, z=z if m == "physics" else None) for m in modules], axis=1)
+    assert list(got_ids) == list(want_ids) and info["files"] == 3 and info["rows"] == len(lc)
+    assert np.array_equal(table.cpu().numpy(), want, equal_nan=True)
+
+
 def test_cache_driver_writes_what_the_trainers_read(golden, features_pkg, tmp_path):
     """features.caches.write_feature_caches on the GPU: every file loads with the reference's structure and holds the
     frames the per-module extractors return"""
