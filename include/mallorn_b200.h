@@ -121,6 +121,38 @@ typedef struct mlrn_inter_op { int32_t kind, a, b, c; double k; } mlrn_inter_op;
 int mlrn_interactions(int device, const double* table, int64_t n_rows, int32_t ld, const mlrn_inter_op* ops, int32_t n_ops,
                       double* out, int32_t ld_out, void* stream);
 
+/* K10 -- histogram gradient-boosted trees on a device-resident table.  Replaces the xgboost
+ * `tree_method='hist'` training of the downstream drivers (non_successful_tests/scripts/train_v92_focal_adversarial.py:
+ * 157-169 parameters, :232-272 5-fold loop; adversarial_validation.py:120-160 the train-vs-test classifier) for the
+ * binary:logistic objective; the focal-loss variants of v92a-c are not covered.  All pointers are DEVICE pointers unless
+ * named *_host; the caller keeps `bins`, `y` and `weight` alive while the handle exists.  The CPU restatement of the same
+ * algorithm (oracle/gbdt.py) grows bit-identical trees. */
+typedef struct mlrn_gbdt mlrn_gbdt;
+typedef struct mlrn_gbdt_params {
+  int32_t max_depth;            /* 1..5                       train_v92...:159 max_depth 5       */
+  double learning_rate;         /*                            :160 0.025                         */
+  double subsample;             /* rows per tree              :161 0.8                           */
+  double min_child_weight;      /*                            :163 3                             */
+  double reg_alpha, reg_lambda; /*                            :164-165 0.2, 1.5                  */
+  double scale_pos_weight;      /* weight of label-1 rows     :240 n_neg / n_pos                 */
+  uint64_t seed;                /* row sub-sampling           :167 random_state 42               */
+} mlrn_gbdt_params;
+/* one tree as a complete binary tree of depth <= 5: node k has children 2k+1 / 2k+2; feature < 0 marks a leaf */
+typedef struct mlrn_gbdt_tree { int32_t feature[63], bin[63], default_left[63]; double value[63]; } mlrn_gbdt_tree;
+/* X [n, ld] float64 -> bins [n, F] uint8: bin b <=> cuts[f][b-1] < x <= cuts[f][b] (at most 254 cuts per feature, row f of
+ * `cuts` [F, 255]), NaN -> 255 (missing). */
+int mlrn_gbdt_bin(int device, const double* X, int64_t n, int32_t F, int32_t ld, const double* cuts, const int32_t* ncuts, uint8_t* bins,
+                  void* stream);
+int mlrn_gbdt_create(int device, const uint8_t* bins, int64_t n, int32_t F, const double* y, const double* weight /* or NULL */,
+                     const mlrn_gbdt_params* params, int32_t max_rounds, void* stream, mlrn_gbdt** out);
+int mlrn_gbdt_destroy(mlrn_gbdt* g);
+/* grow one tree (colmask_host [F]: 1 = column sampled for this tree, colsample_bytree) and add it to the training margins */
+int mlrn_gbdt_round(mlrn_gbdt* g, const uint8_t* colmask_host, void* stream);
+/* margin[i] += sum of trees [tree_from, tree_to) for other rows (validation / test), binned with the same cuts */
+int mlrn_gbdt_predict(const mlrn_gbdt* g, const uint8_t* bins, int64_t n, int32_t tree_from, int32_t tree_to, double* margin, void* stream);
+int mlrn_gbdt_export(const mlrn_gbdt* g, mlrn_gbdt_tree* trees_host, double* train_margin_host);   /* synchronises */
+int32_t mlrn_gbdt_rounds(const mlrn_gbdt* g);
+
 #ifdef __cplusplus
 }
 #endif

@@ -92,7 +92,7 @@ def featurise_shard(cols: dict, n_local: int, modules: Sequence[str], table=None
             rows = torch.empty((n_local, w), dtype=torch.float64, device=f"cuda:{dev}")     # dense rows of this pass; freed (stream-ordered) after the copy
             z = cols.get("z") if m in ("physics", "research") else None
             if z is not None and not (hasattr(z, "is_cuda") and z.is_cuda):
-                z = torch.as_tensor(np.ascontiguousarray(z, dtype=np.float64)).to(f"cuda:{dev}", non_blocking=True)
+                z = torch.from_numpy(np.array(z, dtype=np.float64)).to(f"cuda:{dev}")
             store.features(m, z=z, out=rows, status=(status or {}).get(m))
             table[:, c0:c0 + w].copy_(rows)
             c0 += w

@@ -253,7 +253,18 @@ def oof_f1(X, y, seed, pool=None):
     return float(best), float(best_t), oof
 
 
-def compare_arms(table, rows_cpu, rows_gpu, seeds=(42, 43, 44, 45, 46), pool=None):
+def oof_f1_k10(X, y, seed, weight=None):
+    """The same protocol with the product's own trainer (K10, csrc/gbdt.cu: xgboost-hist restated with the v92d parameters,
+    row and column sub-sampling, L1/L2 regularisation, scale_pos_weight, optional adversarial weights) on the GPU."""
+    import torch
+    from mallorn_astrophysics_b200 import gbdt
+    table = torch.from_numpy(np.ascontiguousarray(X)).cuda()
+    res = gbdt.cross_validate(table, y, weight, gbdt.GBDTParams(seed=seed), 5, 500, 50, use_scale_pos_weight=True, fold_seed=seed)
+    f1, thr = gbdt.best_f1(y, res["oof"], np.linspace(0.05, 0.5, 100))
+    return f1, thr, res["oof"]
+
+
+def compare_arms(table, rows_cpu, rows_gpu, seeds=(42, 43, 44, 45, 46), pool=None, classifier="sklearn", weight=None):
     """The C3 acceptance numbers: OOF F1 of both arms per seed on the 222-column v92d table and on the v34a table."""
     y = (table.metadata_frame()["target"].to_numpy()).astype(int)
     base_c, extra_c = assemble(rows_cpu, table)
@@ -267,8 +278,12 @@ def compare_arms(table, rows_cpu, rows_gpu, seeds=(42, 43, 44, 45, 46), pool=Non
     res = {"objects": int(table.n_obj), "positives": int(y.sum()), "columns": len(names), "base_columns": len(base_cols),
            "high_corr_pairs": int(len(high_corr_df)), "seeds": {}}
     for seed in seeds:
-        fc, tc, _ = oof_f1(Xc, y, seed, pool)
-        fg, tg, _ = oof_f1(Xg, y, seed, pool)
+        if classifier == "k10":
+            fc, tc, _ = oof_f1_k10(Xc, y, seed, weight)
+            fg, tg, _ = oof_f1_k10(Xg, y, seed, weight)
+        else:
+            fc, tc, _ = oof_f1(Xc, y, seed, pool)
+            fg, tg, _ = oof_f1(Xg, y, seed, pool)
         res["seeds"][int(seed)] = {"f1_cpu": fc, "f1_gpu": fg, "delta": fg - fc, "threshold_cpu": tc, "threshold_gpu": tg}
     d = np.array([v["delta"] for v in res["seeds"].values()])
     res["mean_delta"] = float(d.mean())
@@ -279,6 +294,7 @@ def compare_arms(table, rows_cpu, rows_gpu, seeds=(42, 43, 44, 45, 46), pool=Non
     differing = int(np.sum(~np.isclose(Xc, Xg, rtol=1e-3, atol=1e-9, equal_nan=True)))
     res["cells_differing_beyond_1e-3"] = differing
     res["cells"] = int(Xc.size)
-    res["classifier"] = "sklearn HistGradientBoostingClassifier, v34a protocol (xgboost is not installed in this image)"
+    res["classifier"] = ("K10: this library's histogram GBDT on the GPU (csrc/gbdt.cu), v92d parameters and protocol" if classifier == "k10" else
+                         "sklearn HistGradientBoostingClassifier, v34a protocol (xgboost is not installed in this image)")
     res["feature_names"] = names
     return res

@@ -29,6 +29,7 @@ import downstream as D  # noqa: E402
 
 def main():
     n_seeds = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+    classifier = sys.argv[2] if len(sys.argv) > 2 else "sklearn"          # "k10": the product's own GBDT (seconds instead of minutes)
     seeds = tuple(range(42, 42 + n_seeds))
     cores = os.cpu_count() or 1
     t0 = time.time()
@@ -46,8 +47,8 @@ def main():
     t_gpu = time.time() - t0
     print(f"gpu: {t_gpu:.2f} s", file=sys.stderr, flush=True)
     t0 = time.time()
-    res = D.compare_arms(table, rows_cpu, rows_gpu, seeds=seeds, pool=pool)
-    floor = D.compare_arms(table, rows_cpu, rows_libm, seeds=seeds, pool=pool)
+    res = D.compare_arms(table, rows_cpu, rows_gpu, seeds=seeds, pool=pool, classifier=classifier)
+    floor = D.compare_arms(table, rows_cpu, rows_libm, seeds=seeds, pool=pool, classifier=classifier)
     print(f"GBDT protocol, {2 * 2 * len(seeds) * 5} fits: {time.time() - t0:.1f} s", file=sys.stderr, flush=True)
     pool.close()
     res["what"] = ("OOF F1 of the v34a/v92d-style GBDT on GPU features vs CPU (oracle) features, C3 set "

@@ -149,12 +149,12 @@ def test_overlapped_file_pipeline_equals_the_one_shot_path(golden, tmp_path):
         lc.iloc[edges[i]:edges[i + 1]].to_csv(p, index=False)
         paths.append(p)
     modules = ("statistical", "colors", "physics", "bazin")
-    table, got_ids, info = ingest.featurise_files(paths, modules, metadata=meta)
+    table, got_ids, info = ingest.featurise_files(paths, modules, metadata=meta, chunk_bytes=1)      # one group per file
     s, want_ids = LightCurveStore.from_csv(paths)
     with s:
         z = meta.set_index("object_id")["Z"].reindex(list(want_ids)).to_numpy()
         want = np.concatenate([s.features(m, z=z if m == "physics" else None) for m in modules], axis=1)
-    assert list(got_ids) == list(want_ids) and info["files"] == 3 and info["rows"] == len(lc)
+    assert list(got_ids) == list(want_ids) and info["files"] == 3 and info["groups"] == 3 and info["rows"] == len(lc)
     assert np.array_equal(table.cpu().numpy(), want, equal_nan=True)
 
 
