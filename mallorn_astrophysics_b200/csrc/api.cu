@@ -219,7 +219,8 @@ int mlrn_physics(const mlrn_store* s, const double* z, int z_on_device, double* 
   double* ztmp = nullptr;
   if (!z_on_device && s->n_obj > 0) {
     MLRN_CUDA(cudaMallocAsync(&ztmp, sizeof(double) * (size_t)s->n_obj, st));
-    MLRN_CUDA(cudaMemcpyAsync(ztmp, z, sizeof(double) * (size_t)s->n_obj, cudaMemcpyHostToDevice, st));
+    const cudaError_t e = cudaMemcpyAsync(ztmp, z, sizeof(double) * (size_t)s->n_obj, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { cudaFreeAsync(ztmp, st); return mlrn::cuda_fail(e, "host->device copy of the redshift column"); }
     zd = ztmp;
   }
   int rc = with_output(s, out, out_on_device, MLRN_PHYSICS_COLS, st, [&](double* d) { return mlrn::run_physics(s, zd, d, st); });
@@ -235,7 +236,8 @@ int mlrn_research(const mlrn_store* s, const double* z, int z_on_device, double*
   double* ztmp = nullptr;
   if (z && !z_on_device && s->n_obj > 0) {
     MLRN_CUDA(cudaMallocAsync(&ztmp, sizeof(double) * (size_t)s->n_obj, st));
-    MLRN_CUDA(cudaMemcpyAsync(ztmp, z, sizeof(double) * (size_t)s->n_obj, cudaMemcpyHostToDevice, st));
+    const cudaError_t e = cudaMemcpyAsync(ztmp, z, sizeof(double) * (size_t)s->n_obj, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { cudaFreeAsync(ztmp, st); return mlrn::cuda_fail(e, "host->device copy of the redshift column"); }
     zd = ztmp;
   }
   int rc = with_output(s, out, out_on_device, MLRN_RESEARCH_COLS, st, [&](double* d) { return mlrn::run_research(s, zd, d, st); });

@@ -185,10 +185,10 @@ int run_staged(const mlrn_store* s, const P& pol, long long fits, const int* cap
       io.out = stage < n_caps ? buf[stage & 1] : nullptr;
       io.out_count = stage < n_caps ? counts + 2 * stage : nullptr;
       io.out_capacity = capacity;
-      // resumed stages: the survivor count is only known on the device, so they launch the full persistent grid and
-      // every warp reads it; a warp without work leaves at once
-      const long long cgrid = (long long)capacity / FIT_THREADS + 1;
-      const long long grid = stage == 0 ? grid0 : (cgrid < full ? cgrid : full);
+      // resumed stages: the survivor count is only known on the device, so they launch the full persistent grid (every
+      // SM: the survivors are spread over as many warps as there are, a warp's trip costs the union of its lanes' paths)
+      // and every warp reads the count; a warp without work leaves at once
+      const long long grid = stage == 0 ? grid0 : full;
       k_fit_stage<P><<<(int)grid, FIT_THREADS, 0, st>>>(pol, io);
       count_launch();
     }

@@ -38,19 +38,26 @@ def frames_from_store(store, ids, object_ids: Sequence, modules: Sequence[str], 
         counts = store.segments()[:, 0:21:3].sum(axis=1)
     finally:
         store.close()
-    req = _request_index(ids, object_ids)
-    req = req[req >= 0]                              # ids that are not in the store at all
+    req_all = _request_index(ids, object_ids)
+    req = req_all[req_all >= 0]                      # ids that are not in the store at all
     req = req[counts[req] > 0]                       # drop ids with no observations
     id_col = np.asarray(ids, dtype=object)[req]
     frames = {}
     for module in modules:
+        if module == "powerlaw":
+            # the decline-model table has ONE ROW PER REQUESTED ID, NaN where a band cannot be fitted: the reference builds it
+            # by looping over the ids (visualize_and_powerlaw.py:360-371, train_v55_powerlaw.py:196-202), not over a groupby
+            full = np.full((len(req_all), rows[module].shape[1]), np.nan)
+            full[req_all >= 0] = rows[module][req_all[req_all >= 0]]
+            df = pd.DataFrame(full, columns=schema.MODULE_COLUMNS[module])
+            df.insert(0, "object_id", np.asarray(list(object_ids), dtype=object))        # train_v55_powerlaw.py:197
+            frames[module] = df
+            continue
         df = pd.DataFrame(rows[module][req], columns=schema.MODULE_COLUMNS[module])
         if module == "statistical":
             for c in schema.STAT_INT_COLUMNS:
                 df[c] = df[c].astype(np.int64)
             df.insert(0, "object_id", id_col)
-        elif module == "powerlaw":
-            df.insert(0, "object_id", id_col)        # train_v55_powerlaw.py:197
         else:
             df["object_id"] = id_col
         frames[module] = df

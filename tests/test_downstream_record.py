@@ -4,7 +4,7 @@ tests/gpu_downstream_f1.py) and what it supports.
 North star: OOF F1 on the GPU features within 0.005 of the CPU features.  Measured on the C3 set (3,054 labelled objects,
 222-column v92d assembly, 10 seeds): that bound is NOT met per seed -- and it is not met by the reference against ITSELF
 either: swapping numpy's exp for glibc's (<= 1 ulp) in the reference's own Bazin model moves F1 by 0.010 on average and by
-up to 0.019.  The assertions below hold the record to exactly that statement: the GPU arm must stay within a small multiple
+up to 0.019 (0.010 / 0.031 with the K10 trainer).  The assertions below hold the record to exactly that statement: the GPU arm must stay within a small multiple
 of the reference's own noise floor and show no significant systematic shift; they do not pretend the 0.005 bound holds."""
 import json
 import os
@@ -14,8 +14,14 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_downstream_record_is_complete_and_bounded_by_the_reference_noise_floor():
-    rec = json.load(open(os.path.join(ROOT, "profiles", "r02_downstream_f1.json")))
+import pytest
+
+
+@pytest.mark.parametrize("name", ["r02_downstream_f1.json", "r02_downstream_f1_k10.json"])
+def test_downstream_record_is_complete_and_bounded_by_the_reference_noise_floor(name):
+    """Two classifiers over the same three feature arms: scikit-learn's histogram GBDT (the stand-in for xgboost), and the
+    product's own K10 trainer with the v92d parameters (row / column sub-sampling, L1 / L2, scale_pos_weight)."""
+    rec = json.load(open(os.path.join(ROOT, "profiles", name)))
     assert rec["objects"] == 3054 and rec["columns"] == 222 and len(rec["seeds"]) >= 5
     assert len(rec["feature_names"]) == 222 and "all_rise_time" not in rec["feature_names"]
     d = np.array([v["delta"] for v in rec["seeds"].values()])
