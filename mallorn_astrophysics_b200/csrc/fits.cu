@@ -10,6 +10,13 @@
 // machine, so the job struct is the complete state) and picked up by the next stage, which has a higher cap, far fewer
 // fits, and -- once the survivors are fewer than the lanes -- spreads them one per warp, so that the stragglers no longer
 // pay for each other's divergence.  Caps double from stage to stage; the last stage has none.
+//
+// Stragglers.  The last stages hold the fits whose every trip is a Jacobian pass over a long band (40-70 rows x 6 exp):
+// ncu showed them at 1.04 threads per instruction and 224 us per trip -- the latency of ONE thread.  When a resumed stage
+// finds fewer survivors than COOP_FITS_PER_WARP per warp of the grid, it runs them in the COOPERATIVE instantiation of
+// the same solver instead (trf_thread.cuh, COOP = true): one fit per warp, every lane holding the same state, the model
+// evaluations of the rows shared out over the lanes and folded in row order -- the same arithmetic, so which instantiation
+// ran a fit cannot be seen in the result.
 #include <cuda_runtime.h>
 #include <limits.h>
 #include "store.cuh"
@@ -28,6 +35,7 @@ namespace {
 #endif
 constexpr int FIT_THREADS = FIT_THREADS_N;     // warps of one CTA start every trip together (see the barrier in the loop)
 constexpr int MAX_STAGES = 6;
+constexpr int COOP_FITS_PER_WARP = 4;          // a resumed stage with at most this many survivors per warp runs them cooperatively
 
 // a fit that outlived its stage: the whole resumable job and which fit it is
 template <class Job> struct FitCarry { Job job; long long fit; };
@@ -40,8 +48,10 @@ struct StageIo {
 };
 
 // ---- Bazin: fit = band * n_obj + object (band-major: the lanes of a warp get bands of similar length)
-struct BazinPolicy {
-  using Job = BazinJob;
+template <bool COOP>
+struct BazinPolicyT {
+  using Job = BazinJobT<COOP>;
+  using Twin = BazinPolicyT<!COOP>;
   const long long* seg_off; const double *gt, *gf, *ge; int n_obj; double* out; int* status;
   __device__ long long total() const { return (long long)n_obj * N_BAND; }
   __device__ bool start(Job& job, long long fit) const {
@@ -63,9 +73,10 @@ struct BazinPolicy {
 
 // ---- decline models.  KIND 0: the seven fixed-index power laws (21 fits per object); 1: exponential; 2: linear (3 per
 // object each); (band, model)-major fit order: the lanes of a warp fit the same model to the same band of different objects
-template <int KIND>
-struct DeclinePolicy {
-  using Job = DeclineJob<KIND>;
+template <int KIND, bool COOP>
+struct DeclinePolicyT {
+  using Job = DeclineJobT<KIND, COOP>;
+  using Twin = DeclinePolicyT<KIND, !COOP>;
   static constexpr int PER_BAND = (KIND == 0) ? 7 : 1;
   const long long* seg_off; const double *gt, *gf; int n_obj; double* out; int* status;
   __device__ long long total() const { return (long long)n_obj * 3 * PER_BAND; }
@@ -94,17 +105,24 @@ struct DeclinePolicy {
   }
 };
 
-template <class P>
-__global__ void __launch_bounds__(FIT_THREADS, FIT_MIN_BLOCKS) k_fit_stage(P pol, StageIo io) {
+template <bool C> BazinPolicyT<!C> twin(const BazinPolicyT<C>& p) { return {p.seg_off, p.gt, p.gf, p.ge, p.n_obj, p.out, p.status}; }
+template <int K, bool C> DeclinePolicyT<K, !C> twin(const DeclinePolicyT<K, C>& p) { return {p.seg_off, p.gt, p.gf, p.n_obj, p.out, p.status}; }
+
+// COOP = false: one thread per fit.  COOP = true: one WARP per fit (resumed stages only); `coop_limit`: the largest survivor
+// count the cooperative launch takes -- the two launches of a resumed stage read the same count and exactly one of them works.
+template <class P, bool COOP>
+__global__ void __launch_bounds__(FIT_THREADS, FIT_MIN_BLOCKS) k_fit_stage(P pol, StageIo io, long long coop_limit) {
   using Job = typename P::Job;
   using Carry = FitCarry<Job>;
   const Carry* in = (const Carry*)io.in;
   Carry* outc = (Carry*)io.out;
+  const int lane = threadIdx.x & 31;
   long long total;
-  int lanes = 32;                                     // lanes of a warp that take work
+  int lanes = 32;                                     // lanes of a warp that take work (thread mode)
   if (in) {
     const unsigned c = *io.in_count;
     total = c < io.in_capacity ? c : io.in_capacity;
+    if (COOP ? (total > coop_limit) : (total <= coop_limit)) return;      // the other instantiation's stage
     const long long warps = (long long)gridDim.x * (FIT_THREADS / 32);
     const long long per_warp = (total + warps - 1) / warps;      // fewer survivors than lanes: spread them over the warps
     lanes = per_warp < 1 ? 1 : (per_warp > 32 ? 32 : (int)per_warp);
@@ -112,25 +130,31 @@ __global__ void __launch_bounds__(FIT_THREADS, FIT_MIN_BLOCKS) k_fit_stage(P pol
     total = pol.total();
   }
   Job job;
-  bool active = false, exhausted = (int)(threadIdx.x & 31) >= lanes, may_export = outc != nullptr;
+  bool active = false, exhausted = !COOP && lane >= lanes, may_export = outc != nullptr;
   long long fit = 0;
   for (;;) {
     for (int tries = 0; tries < 4 && !active && !exhausted; ++tries) {
-      const long long tk = (long long)atomicAdd(io.ticket, 1ULL);
+      long long tk = 0;
+      if (!COOP || lane == 0) tk = (long long)atomicAdd(io.ticket, 1ULL);
+      if (COOP) tk = __shfl_sync(0xffffffffu, tk, 0);               // one ticket per warp
       if (tk >= total) { exhausted = true; break; }
       if (in) { job = in[tk].job; fit = in[tk].fit; active = true; }
       else { fit = tk; active = pol.start(job, fit); }
     }
     if (!__syncthreads_or(active || !exhausted)) break;      // also lines the warps up: they fetch the same code
     if (active) {
-      const int rc = job.step();
+      const int rc = job.step();                      // COOP: every lane advances the same fit (uniform control flow)
       if (rc != TRF_RUNNING) {
-        pol.done(job, fit, rc);
+        if (!COOP || lane == 0) pol.done(job, fit, rc);
         active = false;
       } else if (may_export && job.trf.nfev >= io.cap) {
-        const unsigned slot = atomicAdd(io.out_count, 1u);
-        if (slot < io.out_capacity) { outc[slot].job = job; outc[slot].fit = fit; active = false; }
-        else may_export = false;                      // carry buffer full: finish here
+        unsigned slot = 0;
+        if (!COOP || lane == 0) slot = atomicAdd(io.out_count, 1u);
+        if (COOP) slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (slot < io.out_capacity) {
+          if (!COOP || lane == 0) { outc[slot].job = job; outc[slot].fit = fit; }
+          active = false;
+        } else may_export = false;                    // carry buffer full: finish here
       }
     }
   }
@@ -157,8 +181,11 @@ __global__ void k_bazin_tail(int n_obj, double* __restrict__ out) {
 template <class P>
 int run_staged(const mlrn_store* s, const P& pol, long long fits, const int* caps, int n_caps, double carry_frac, cudaStream_t st) {
   using Carry = FitCarry<typename P::Job>;
+  using PC = typename P::Twin;                         // the cooperative instantiation: same members, same carry layout
+  static_assert(sizeof(FitCarry<typename PC::Job>) == sizeof(Carry), "carry records of the two instantiations must be interchangeable");
+  const PC polc = twin(pol);
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fit_stage<P>, FIT_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fit_stage<P, false>, FIT_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
   const long long full = (long long)s->sm_count * per_sm;
   long long want = (fits + FIT_THREADS - 1) / FIT_THREADS;
   const int grid0 = (int)(want < full ? (want > 0 ? want : 1) : full);
@@ -189,8 +216,13 @@ int run_staged(const mlrn_store* s, const P& pol, long long fits, const int* cap
       // SM: the survivors are spread over as many warps as there are, a warp's trip costs the union of its lanes' paths)
       // and every warp reads the count; a warp without work leaves at once
       const long long grid = stage == 0 ? grid0 : full;
-      k_fit_stage<P><<<(int)grid, FIT_THREADS, 0, st>>>(pol, io);
+      const long long coop_limit = stage == 0 ? -1 : full * (FIT_THREADS / 32) * COOP_FITS_PER_WARP;
+      k_fit_stage<P, false><<<(int)grid, FIT_THREADS, 0, st>>>(pol, io, coop_limit);
       count_launch();
+      if (stage > 0) {
+        k_fit_stage<PC, true><<<(int)full, FIT_THREADS, 0, st>>>(polc, io, coop_limit);
+        count_launch();
+      }
     }
     e = cudaGetLastError();
   }
@@ -213,7 +245,7 @@ int run_staged(const mlrn_store* s, const P& pol, long long fits, const int* cap
 int run_bazin(const mlrn_store* s, double* out_dev, int* status_dev, cudaStream_t st) {
   if (s->n_obj == 0) return MLRN_OK;
   const int caps[] = FIT_STAGE_CAPS;
-  BazinPolicy pol{s->seg_off, s->t, s->flux, s->err, s->n_obj, out_dev, status_dev};
+  BazinPolicyT<false> pol{s->seg_off, s->t, s->flux, s->err, s->n_obj, out_dev, status_dev};
   const int rc = run_staged(s, pol, (long long)s->n_obj * N_BAND, caps, (int)(sizeof(caps) / sizeof(int)), 0.15, st);
   if (rc != MLRN_OK) return rc;
   k_bazin_tail<<<(s->n_obj + 255) / 256, 256, 0, st>>>(s->n_obj, out_dev);
@@ -226,9 +258,9 @@ int run_powerlaw(const mlrn_store* s, double* out_dev, int* status_dev, cudaStre
   if (s->n_obj == 0) return MLRN_OK;
   const int caps[] = FIT_DECLINE_CAPS;
   const int n_caps = (int)(sizeof(caps) / sizeof(int));
-  int rc = run_staged(s, DeclinePolicy<0>{s->seg_off, s->t, s->flux, s->n_obj, out_dev, status_dev}, (long long)s->n_obj * 21, caps, n_caps, 0.10, st);
-  if (rc == MLRN_OK) rc = run_staged(s, DeclinePolicy<1>{s->seg_off, s->t, s->flux, s->n_obj, out_dev, status_dev}, (long long)s->n_obj * 3, caps, n_caps, 0.10, st);
-  if (rc == MLRN_OK) rc = run_staged(s, DeclinePolicy<2>{s->seg_off, s->t, s->flux, s->n_obj, out_dev, status_dev}, (long long)s->n_obj * 3, caps, n_caps, 0.10, st);
+  int rc = run_staged(s, DeclinePolicyT<0, false>{s->seg_off, s->t, s->flux, s->n_obj, out_dev, status_dev}, (long long)s->n_obj * 21, caps, n_caps, 0.10, st);
+  if (rc == MLRN_OK) rc = run_staged(s, DeclinePolicyT<1, false>{s->seg_off, s->t, s->flux, s->n_obj, out_dev, status_dev}, (long long)s->n_obj * 3, caps, n_caps, 0.10, st);
+  if (rc == MLRN_OK) rc = run_staged(s, DeclinePolicyT<2, false>{s->seg_off, s->t, s->flux, s->n_obj, out_dev, status_dev}, (long long)s->n_obj * 3, caps, n_caps, 0.10, st);
   return rc;
 }
 

@@ -24,8 +24,9 @@ MLRN_FN double median_unsorted(const double* a, int n) {
   return (n & 1) ? hi : 0.5 * (lo + hi);
 }
 
-struct BazinJob {
-  TrfThread<5, BazinModel> trf;
+template <bool COOP>
+struct BazinJobT {
+  TrfThread<5, BazinModel, COOP> trf;
   const double *t, *f, *e; int n;
 
   // Returns true if the fit is running; otherwise `code` is final (skipped / bad input / infeasible start).
@@ -59,6 +60,8 @@ struct BazinJob {
   }
 };
 
+using BazinJob = BazinJobT<false>;
+
 // decline models on the post-peak suffix of a time-sorted band: x_i = t_i - t_peak, y_i = f_i
 struct PowerModelT {
   const double* t; const double* y; double pt, k;
@@ -85,11 +88,11 @@ template <> struct DeclineTraits<0> { static constexpr int NP = 2; using Model =
 template <> struct DeclineTraits<1> { static constexpr int NP = 3; using Model = ExpModelT; };
 template <> struct DeclineTraits<2> { static constexpr int NP = 3; using Model = LinModelT; };
 
-template <int KIND>
-struct DeclineJob {
+template <int KIND, bool COOP>
+struct DeclineJobT {
   static constexpr int NP = DeclineTraits<KIND>::NP;
   using Model = typename DeclineTraits<KIND>::Model;
-  TrfThread<NP, Model> trf;
+  TrfThread<NP, Model, COOP> trf;
   Model mdl; int m; double ss_tot;
 
   MLRN_FN bool init(const double* t, const double* f, int n, double kpow, int& code) {
@@ -124,6 +127,8 @@ struct DeclineJob {
     return (ss_tot > 0.0) ? 1.0 - ss / ss_tot : 0.0;                           // :186-189
   }
 };
+
+template <int KIND> using DeclineJob = DeclineJobT<KIND, false>;
 
 MLRN_FN double decline_index(int q) {                                          // MODELS order (:135-145)
   const double kk[7] = {-5.0 / 3.0, -1.0, -1.5, -2.0, -2.5, -3.0, -0.5};

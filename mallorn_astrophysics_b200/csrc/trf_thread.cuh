@@ -65,7 +65,12 @@ MLRN_FN double generic_fd_row(const Model& mdl, int i, const double* x, const do
   return r0;
 }
 
-template <int NP, class Model>
+// COOP = false: one thread per fit.  COOP = true (device only): the 32 lanes of a warp hold the SAME fit -- identical
+// state in every lane, uniform control flow -- and share out the only part that is per-row and expensive, the model
+// evaluations: lane l evaluates rows l, l+32, ...; the values are then broadcast and folded into the cost / the triangular
+// factor by every lane in row order, i.e. with exactly the arithmetic of the one-thread solver (bit-identical results).
+// Used for the stragglers of the staged fit kernels (fits.cu), whose trips are dominated by 40-70 rows x 6 exp().
+template <int NP, class Model, bool COOP = false>
 struct TrfThread {
   // problem
   Model mdl; int m, max_nfev;
@@ -79,6 +84,19 @@ struct TrfThread {
 
   MLRN_NOINLINE double residual_cost(const double* xx, bool& finite) const {
     double acc = 0.0; bool bad = false;
+#ifdef __CUDA_ARCH__
+    if (COOP) {
+      const int lane = threadIdx.x & 31;
+      for (int base = 0; base < m; base += 32) {
+        const int i = base + lane;
+        const double mine = (i < m) ? mdl.resid(i, xx) : 0.0;
+        const int cnt = (m - base < 32) ? m - base : 32;
+        for (int j = 0; j < cnt; ++j) { const double r = __shfl_sync(0xffffffffu, mine, j); acc += r * r; bad = bad || !is_finite(r); }
+      }
+      finite = !bad;
+      return 0.5 * acc;
+    }
+#endif
     for (int i = 0; i < m; ++i) { const double r = mdl.resid(i, xx); acc += r * r; bad = bad || !is_finite(r); }
     finite = !bad;
     return 0.5 * acc;
@@ -134,6 +152,25 @@ struct TrfThread {
     }
     F0.clear();
     bool bad = false;
+#ifdef __CUDA_ARCH__
+    if (COOP) {
+      const int lane = threadIdx.x & 31;
+      for (int base = 0; base < m; base += 32) {
+        const int i = base + lane;
+        double mine[NP], r_mine = 0.0;
+#pragma unroll
+        for (int c = 0; c < NP; ++c) mine[c] = 0.0;
+        if (i < m) r_mine = mdl.fd_row(i, x, xpd, dx, mine);
+        const int cnt = (m - base < 32) ? m - base : 32;
+        for (int j = 0; j < cnt; ++j) {
+          double row[NP];
+#pragma unroll
+          for (int c = 0; c < NP; ++c) { row[c] = __shfl_sync(0xffffffffu, mine[c], j); bad = bad || !is_finite(row[c]); }
+          F0.add_row(row, __shfl_sync(0xffffffffu, r_mine, j));
+        }
+      }
+    } else
+#endif
     for (int i = 0; i < m; ++i) {
       double row[NP];
       const double r0 = mdl.fd_row(i, x, xpd, dx, row);
