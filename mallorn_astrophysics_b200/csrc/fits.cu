@@ -17,8 +17,16 @@
 // the same solver instead (trf_thread.cuh, COOP = true): one fit per warp, every lane holding the same state, the model
 // evaluations of the rows shared out over the lanes and folded in row order -- the same arithmetic, so which instantiation
 // ran a fit cannot be seen in the result.
+//
+// Work order.  A trip of a warp costs the LONGEST of its lanes' row loops (Jacobian pass and trial evaluation both run over
+// the rows of the fit), and in (band, object) order the lanes of a warp hold bands of 10-50 rows side by side -- decline
+// fits, whose rows are the post-peak suffix, anything from 3 rows to the whole band.  Stage 0 therefore takes its fits from
+// a list sorted by row count, longest first (counting sort: histogram, one-block scan, scatter): lanes that work side by
+// side have the same loop lengths, and the long fits do not start last.  The order inside a bucket is whatever the atomics
+// give; the result of a fit does not depend on when or where it runs.
 #include <cuda_runtime.h>
 #include <limits.h>
+#include <stdlib.h>
 #include "store.cuh"
 #include "fits.cuh"
 #include "fits_thread.cuh"
@@ -41,6 +49,7 @@ constexpr int COOP_FITS_PER_WARP = 4;          // a resumed stage with at most t
 template <class Job> struct FitCarry { Job job; long long fit; };
 
 struct StageIo {
+  const unsigned* order;            // stage 0: ticket -> fit (sorted by row count, longest first); nullptr: ticket = fit
   unsigned long long* ticket;        // this stage's work counter
   int cap;                           // function evaluations after which a running fit moves on (INT_MAX: never)
   const void* in; const unsigned* in_count; unsigned in_capacity;       // carried fits to resume (nullptr: fresh fits)
@@ -54,6 +63,10 @@ struct BazinPolicyT {
   using Twin = BazinPolicyT<!COOP>;
   const long long* seg_off; const double *gt, *gf, *ge; int n_obj; double* out; int* status;
   __device__ long long total() const { return (long long)n_obj * N_BAND; }
+  __device__ int rows(long long fit) const {                            // rows of the fit (work-order key)
+    const int b = (int)(fit / n_obj); const long long o = fit % n_obj;
+    return (int)(seg_off[o * N_SEG + b + 1] - seg_off[o * N_SEG + b]);
+  }
   __device__ bool start(Job& job, long long fit) const {
     const int b = (int)(fit / n_obj); const long long o = fit % n_obj;
     const long long lo = seg_off[o * N_SEG + b];
@@ -78,8 +91,15 @@ struct DeclinePolicyT {
   using Job = DeclineJobT<KIND, COOP>;
   using Twin = DeclinePolicyT<KIND, !COOP>;
   static constexpr int PER_BAND = (KIND == 0) ? 7 : 1;
-  const long long* seg_off; const double *gt, *gf; int n_obj; double* out; int* status;
+  const long long* seg_off; const double *gt, *gf; int n_obj; double* out; int* status; const int* meta;
   __device__ long long total() const { return (long long)n_obj * 3 * PER_BAND; }
+  __device__ int rows(long long fit) const {                            // observations after the peak (estimate: ties in time ignored)
+    const int rem = (int)(fit / n_obj); const long long o = fit % n_obj;
+    const int j = rem / PER_BAND;
+    const int band = (j == 0) ? BG : (j == 1 ? BR : BI);
+    const int n = meta[o * 22 + 3 * band], pk = meta[o * 22 + 3 * band + 2];
+    return (n < 5 || pk < 0) ? 0 : n - pk - 1;
+  }
   __device__ long long slot(long long fit) const {                      // column of this fit inside the 27-wide row
     const int rem = (int)(fit / n_obj); const long long o = fit % n_obj;
     const int j = rem / PER_BAND, q = (KIND == 0) ? rem % PER_BAND : (KIND == 1 ? 7 : 8);
@@ -106,10 +126,51 @@ struct DeclinePolicyT {
 };
 
 template <bool C> BazinPolicyT<!C> twin(const BazinPolicyT<C>& p) { return {p.seg_off, p.gt, p.gf, p.ge, p.n_obj, p.out, p.status}; }
-template <int K, bool C> DeclinePolicyT<K, !C> twin(const DeclinePolicyT<K, C>& p) { return {p.seg_off, p.gt, p.gf, p.n_obj, p.out, p.status}; }
+template <int K, bool C> DeclinePolicyT<K, !C> twin(const DeclinePolicyT<K, C>& p) { return {p.seg_off, p.gt, p.gf, p.n_obj, p.out, p.status, p.meta}; }
+
+// ---- work order: counting sort of the fits by row count, longest first
+constexpr int ORDER_BINS = 1024;
+template <class P>
+__global__ void __launch_bounds__(256) k_fit_hist(P pol, unsigned* __restrict__ hist) {
+  __shared__ unsigned sh[ORDER_BINS];
+  for (int i = threadIdx.x; i < ORDER_BINS; i += blockDim.x) sh[i] = 0u;
+  __syncthreads();
+  const long long total = pol.total();
+  for (long long fit = blockIdx.x * (long long)blockDim.x + threadIdx.x; fit < total; fit += (long long)gridDim.x * blockDim.x) {
+    const int r = pol.rows(fit);
+    atomicAdd(&sh[r < ORDER_BINS ? r : ORDER_BINS - 1], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ORDER_BINS; i += blockDim.x) if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+// cursor[k] = number of fits with more rows than k (one block of ORDER_BINS threads)
+__global__ void __launch_bounds__(ORDER_BINS) k_fit_scan(const unsigned* __restrict__ hist, unsigned* __restrict__ cursor) {
+  __shared__ unsigned sh[ORDER_BINS];
+  const int k = threadIdx.x;
+  sh[k] = hist[ORDER_BINS - 1 - k];                    // descending keys
+  __syncthreads();
+  for (int d = 1; d < ORDER_BINS; d <<= 1) {
+    const unsigned v = (k >= d) ? sh[k - d] : 0u;
+    __syncthreads();
+    sh[k] += v;
+    __syncthreads();
+  }
+  cursor[ORDER_BINS - 1 - k] = sh[k] - hist[ORDER_BINS - 1 - k];
+}
+template <class P>
+__global__ void __launch_bounds__(256) k_fit_scatter(P pol, unsigned* __restrict__ cursor, unsigned* __restrict__ order) {
+  const long long total = pol.total();
+  for (long long fit = blockIdx.x * (long long)blockDim.x + threadIdx.x; fit < total; fit += (long long)gridDim.x * blockDim.x) {
+    const int r = pol.rows(fit);
+    order[atomicAdd(&cursor[r < ORDER_BINS ? r : ORDER_BINS - 1], 1u)] = (unsigned)fit;
+  }
+}
 
 // COOP = false: one thread per fit.  COOP = true: one WARP per fit (resumed stages only); `coop_limit`: the largest survivor
 // count the cooperative launch takes -- the two launches of a resumed stage read the same count and exactly one of them works.
+#ifdef FIT_STATS
+__device__ unsigned long long g_fit_stats[8];   // warp trips, active lanes, lanes with a Jacobian pass, rows (sum, max), rows of the passes (sum, max), trips with a pass
+#endif
 template <class P, bool COOP>
 __global__ void __launch_bounds__(FIT_THREADS, FIT_MIN_BLOCKS) k_fit_stage(P pol, StageIo io, long long coop_limit) {
   using Job = typename P::Job;
@@ -130,6 +191,7 @@ __global__ void __launch_bounds__(FIT_THREADS, FIT_MIN_BLOCKS) k_fit_stage(P pol
     total = pol.total();
   }
   Job job;
+  job.trf.need_jac = false;
   bool active = false, exhausted = !COOP && lane >= lanes, may_export = outc != nullptr;
   long long fit = 0;
   for (;;) {
@@ -139,9 +201,27 @@ __global__ void __launch_bounds__(FIT_THREADS, FIT_MIN_BLOCKS) k_fit_stage(P pol
       if (COOP) tk = __shfl_sync(0xffffffffu, tk, 0);               // one ticket per warp
       if (tk >= total) { exhausted = true; break; }
       if (in) { job = in[tk].job; fit = in[tk].fit; active = true; }
-      else { fit = tk; active = pol.start(job, fit); }
+      else { fit = io.order ? (long long)io.order[tk] : tk; active = pol.start(job, fit); }
     }
     if (!__syncthreads_or(active || !exhausted)) break;      // also lines the warps up: they fetch the same code
+#ifdef FIT_STATS
+    if (!COOP) {                                       // developer build: where do the lanes of a trip stand?
+      const bool nj = active && job.trf.need_jac;
+      const int mm = active ? job.trf.m : 0;
+      const int n_act = __popc(__ballot_sync(0xffffffffu, active)), n_jac = __popc(__ballot_sync(0xffffffffu, nj));
+      const int sum_m = __reduce_add_sync(0xffffffffu, mm), max_m = __reduce_max_sync(0xffffffffu, mm);
+      const int sum_mj = __reduce_add_sync(0xffffffffu, nj ? mm : 0), max_mj = __reduce_max_sync(0xffffffffu, nj ? mm : 0);
+      if (lane == 0 && n_act > 0) {
+        atomicAdd(&g_fit_stats[0], 1ULL); atomicAdd(&g_fit_stats[1], (unsigned long long)n_act); atomicAdd(&g_fit_stats[2], (unsigned long long)n_jac);
+        atomicAdd(&g_fit_stats[3], (unsigned long long)sum_m); atomicAdd(&g_fit_stats[4], (unsigned long long)max_m);
+        atomicAdd(&g_fit_stats[5], (unsigned long long)sum_mj); atomicAdd(&g_fit_stats[6], (unsigned long long)max_mj);
+        if (n_jac > 0) atomicAdd(&g_fit_stats[7], 1ULL);
+      }
+    }
+#endif
+#ifndef TRF_NO_LEND
+    if (!COOP) job.trf.jacobian_warp(active && job.trf.need_jac);      // every lane: those without a pass of their own lend a hand
+#endif
     if (active) {
       const int rc = job.step();                      // COOP: every lane advances the same fit (uniform control flow)
       if (rc != TRF_RUNNING) {
@@ -196,14 +276,29 @@ int run_staged(const mlrn_store* s, const P& pol, long long fits, const int* cap
   const unsigned capacity = (unsigned)(cap_l < 0xffffffffLL ? cap_l : 0xffffffffLL);
   unsigned long long* ctr = nullptr;                  // [MAX_STAGES] tickets, then [MAX_STAGES] carry counts (as unsigned)
   Carry* buf[2] = {nullptr, nullptr};
+  unsigned* order = nullptr;                          // [fits] the work order of stage 0, then [ORDER_BINS] histogram + [ORDER_BINS] cursors
   MLRN_CUDA(cudaMallocAsync(&ctr, sizeof(unsigned long long) * 2 * MAX_STAGES, st));
   cudaError_t e = cudaMemsetAsync(ctr, 0, sizeof(unsigned long long) * 2 * MAX_STAGES, st);
+  if (e == cudaSuccess && fits > 64 && fits < 0xffffffffLL && !getenv("MLRN_FIT_UNORDERED")) {
+    e = cudaMallocAsync(&order, sizeof(unsigned) * ((size_t)fits + 2 * ORDER_BINS), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(order + fits, 0, sizeof(unsigned) * 2 * ORDER_BINS, st);
+    if (e == cudaSuccess) {
+      long long blocks = (fits + 256 * 8 - 1) / (256 * 8);
+      if (blocks > s->sm_count * 8) blocks = s->sm_count * 8;
+      k_fit_hist<P><<<(int)blocks, 256, 0, st>>>(pol, order + fits);
+      k_fit_scan<<<1, ORDER_BINS, 0, st>>>(order + fits, order + fits + ORDER_BINS);
+      k_fit_scatter<P><<<(int)blocks, 256, 0, st>>>(pol, order + fits + ORDER_BINS, order);
+      count_launch(3);
+      e = cudaGetLastError();
+    }
+  }
   if (e == cudaSuccess && n_caps > 0) e = cudaMallocAsync(&buf[0], sizeof(Carry) * (size_t)capacity, st);
   if (e == cudaSuccess && n_caps > 1) e = cudaMallocAsync(&buf[1], sizeof(Carry) * (size_t)capacity, st);
   if (e == cudaSuccess) {
     unsigned* counts = (unsigned*)(ctr + MAX_STAGES);
     for (int stage = 0; stage <= n_caps; ++stage) {
       StageIo io;
+      io.order = stage == 0 ? order : nullptr;
       io.ticket = ctr + stage;
       io.cap = stage < n_caps ? caps[stage] : INT_MAX;
       io.in = stage > 0 ? buf[(stage - 1) & 1] : nullptr;
@@ -228,10 +323,21 @@ int run_staged(const mlrn_store* s, const P& pol, long long fits, const int* cap
   }
   if (buf[0]) cudaFreeAsync(buf[0], st);
   if (buf[1]) cudaFreeAsync(buf[1], st);
+  if (order) cudaFreeAsync(order, st);
   cudaFreeAsync(ctr, st);
   if (e != cudaSuccess) return cuda_fail(e, "staged fit launch");
   return MLRN_OK;
 }
+
+#ifdef FIT_STATS
+}  // namespace
+extern "C" void mlrn_fit_stats(unsigned long long* out8, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out8, g_fit_stats, sizeof(unsigned long long) * 8);
+  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_fit_stats, z, sizeof(z)); }
+}
+namespace {
+#endif
 
 #ifndef FIT_STAGE_CAPS
 #define FIT_STAGE_CAPS {128, 256, 512, 1024}
@@ -258,9 +364,9 @@ int run_powerlaw(const mlrn_store* s, double* out_dev, int* status_dev, cudaStre
   if (s->n_obj == 0) return MLRN_OK;
   const int caps[] = FIT_DECLINE_CAPS;
   const int n_caps = (int)(sizeof(caps) / sizeof(int));
-  int rc = run_staged(s, DeclinePolicyT<0, false>{s->seg_off, s->t, s->flux, s->n_obj, out_dev, status_dev}, (long long)s->n_obj * 21, caps, n_caps, 0.10, st);
-  if (rc == MLRN_OK) rc = run_staged(s, DeclinePolicyT<1, false>{s->seg_off, s->t, s->flux, s->n_obj, out_dev, status_dev}, (long long)s->n_obj * 3, caps, n_caps, 0.10, st);
-  if (rc == MLRN_OK) rc = run_staged(s, DeclinePolicyT<2, false>{s->seg_off, s->t, s->flux, s->n_obj, out_dev, status_dev}, (long long)s->n_obj * 3, caps, n_caps, 0.10, st);
+  int rc = run_staged(s, DeclinePolicyT<0, false>{s->seg_off, s->t, s->flux, s->n_obj, out_dev, status_dev, s->seg_meta}, (long long)s->n_obj * 21, caps, n_caps, 0.10, st);
+  if (rc == MLRN_OK) rc = run_staged(s, DeclinePolicyT<1, false>{s->seg_off, s->t, s->flux, s->n_obj, out_dev, status_dev, s->seg_meta}, (long long)s->n_obj * 3, caps, n_caps, 0.10, st);
+  if (rc == MLRN_OK) rc = run_staged(s, DeclinePolicyT<2, false>{s->seg_off, s->t, s->flux, s->n_obj, out_dev, status_dev, s->seg_meta}, (long long)s->n_obj * 3, caps, n_caps, 0.10, st);
   return rc;
 }
 

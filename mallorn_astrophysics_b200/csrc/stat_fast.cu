@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include "store.cuh"
 #include "stat.cuh"
+#include "stat_warp.cuh"
 #include "../../include/mallorn_b200.h"
 
 namespace mlrn {
@@ -174,9 +175,10 @@ __host__ __device__ inline size_t sf_warp_doubles(int cap) { return 5 * (size_t)
 
 __global__ void __launch_bounds__(SF_WARPS_MAX * 32)
 k_stat(const long long* __restrict__ seg_off, const double* __restrict__ gt, const double* __restrict__ gf,
-       const double* __restrict__ ge, const unsigned short* __restrict__ gtrank, ObjClass cls, int cap,
-       double* __restrict__ out) {
+       const double* __restrict__ ge, const unsigned short* __restrict__ gtrank, ObjClass cls, const int* __restrict__ list_count,
+       int cap, double* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem[];
+  if (list_count) cls.count = *list_count;            // a list made on the device by the launch before (k_stat_warp)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   double* row = cls.scratch ? (double*)cls.scratch + ((size_t)blockIdx.x * nwarps + warp) * sf_warp_doubles(cap)
                             : (double*)smem + (size_t)warp * sf_warp_doubles(cap);
@@ -297,6 +299,27 @@ k_stat(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
   }
 }
 
+// The ordinary objects (at most 255 observations): stat_warp.cuh.  What it declines -- longer short objects, non-finite
+// values -- goes on `fb_list` for k_stat above; objects beyond SHORT_LIMIT are the long-object launch's.
+constexpr int SW_WARPS = 4;
+#ifndef SW_MIN_BLOCKS
+#define SW_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(SW_WARPS * 32, SW_MIN_BLOCKS)
+k_stat_warp(const long long* __restrict__ seg_off, const double* __restrict__ gt, const double* __restrict__ gf,
+            const double* __restrict__ ge, const unsigned short* __restrict__ gtrank, int n_obj, double* __restrict__ out,
+            int* __restrict__ fb_list, int* __restrict__ fb_count) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  statw::WarpSmem& w = reinterpret_cast<statw::WarpSmem*>(smem)[warp];
+  for (long long o = (long long)blockIdx.x * SW_WARPS + warp; o < n_obj; o += (long long)gridDim.x * SW_WARPS) {
+    if (!statw::stat_object(w, seg_off, gt, gf, ge, gtrank, o, lane, out)) {
+      if (lane == 0 && (int)(seg_off[(o + 1) * N_SEG] - seg_off[o * N_SEG]) <= SHORT_LIMIT) fb_list[atomicAdd(fb_count, 1)] = (int)o;
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace
 
 // staging capacity per warp for objects of at most `longest` observations with segments of at most `seg`: the object, and
@@ -310,30 +333,53 @@ static int stat_cap(int longest, int seg) {
 
 int run_stat(const mlrn_store* s, double* out_dev, cudaStream_t st) {
   if (s->n_obj == 0) return MLRN_OK;
-  // short objects: shared-memory staging sized by the longest of them (not by the longest object of the batch: one
-  // 3,000-point object used to push every warp's slice to the point where a single warp fitted on an SM)
-  const int cap = stat_cap(s->max_short, s->max_seg < s->max_short ? s->max_seg : s->max_short);
-  int warps = 4;
-  while (warps > 1 && sf_warp_doubles(cap) * sizeof(double) * warps > 56 * 1024) warps >>= 1;
-  const size_t smem = sf_warp_doubles(cap) * sizeof(double) * warps;
-  MLRN_CUDA(cudaFuncSetAttribute(k_stat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0;
-  MLRN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stat, warps * 32, smem));
-  if (per_sm < 1) per_sm = 1;
-  long long want = ((long long)s->n_obj + warps - 1) / warps;
-  long long capg = (long long)s->sm_count * per_sm;
-  const int grid = (int)(want < capg ? want : capg);
-  k_stat<<<grid, warps * 32, smem, st>>>(s->seg_off, s->t, s->flux, s->err, s->trank, ObjClass{nullptr, s->n_obj, SHORT_LIMIT, nullptr}, cap, out_dev);
-  MLRN_CUDA(cudaGetLastError());
-  count_launch();
+  // ---- launch 1: every object of at most 255 observations (stat_warp.cuh); the others up to SHORT_LIMIT are listed
+  int* fb = nullptr;                                  // [0] = count, [1..] = the listed objects
+  MLRN_CUDA(cudaMallocAsync(&fb, sizeof(int) * ((size_t)s->n_obj + 1), st));
+  auto fail = [&](cudaError_t e, const char* what) { cudaFreeAsync(fb, st); return cuda_fail(e, what); };
+  cudaError_t e = cudaMemsetAsync(fb, 0, sizeof(int), st);
+  if (e != cudaSuccess) return fail(e, "cudaMemsetAsync (k_stat_warp list)");
+  {
+    const size_t smem = sizeof(statw::WarpSmem) * SW_WARPS;
+    e = cudaFuncSetAttribute(k_stat_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(e, "cudaFuncSetAttribute (k_stat_warp)");
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stat_warp, SW_WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const long long want = ((long long)s->n_obj + SW_WARPS - 1) / SW_WARPS, capg = (long long)s->sm_count * per_sm;
+    k_stat_warp<<<(int)(want < capg ? want : capg), SW_WARPS * 32, smem, st>>>(s->seg_off, s->t, s->flux, s->err, s->trank, s->n_obj, out_dev, fb + 1, fb);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(e, "k_stat_warp launch");
+    count_launch();
+  }
+  // ---- launch 2: the listed objects with the general kernel, shared-memory staging sized by the longest short object (not
+  // by the longest object of the batch: one 3,000-point object used to push every warp's slice to the point where a single
+  // warp fitted on an SM).  The list is normally empty (the count is read on the device): a small grid then.
+  {
+    const int cap = stat_cap(s->max_short, s->max_seg < s->max_short ? s->max_seg : s->max_short);
+    int warps = 4;
+    while (warps > 1 && sf_warp_doubles(cap) * sizeof(double) * warps > 56 * 1024) warps >>= 1;
+    const size_t smem = sf_warp_doubles(cap) * sizeof(double) * warps;
+    e = cudaFuncSetAttribute(k_stat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(e, "cudaFuncSetAttribute (k_stat)");
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stat, warps * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    long long want = ((long long)s->n_obj + warps - 1) / warps;
+    long long capg = (long long)s->sm_count * (s->max_short >= statw::CAP ? per_sm : 1);
+    const int grid = (int)(want < capg ? want : capg);
+    k_stat<<<grid, warps * 32, smem, st>>>(s->seg_off, s->t, s->flux, s->err, s->trank, ObjClass{fb + 1, 0, SHORT_LIMIT, nullptr}, fb, cap, out_dev);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(e, "k_stat launch");
+    count_launch();
+  }
+  cudaFreeAsync(fb, st);
   if (s->n_long > 0) {                                // long objects: staging in a per-warp global scratch
     const int capl = stat_cap(s->max_obs, s->max_seg);
     int gl = (s->n_long + 3) / 4;
     if (gl > s->sm_count * 2) gl = s->sm_count * 2;
     unsigned char* scratch = nullptr;
     MLRN_CUDA(cudaMallocAsync(&scratch, sf_warp_doubles(capl) * sizeof(double) * 4 * (size_t)gl, st));
-    k_stat<<<gl, 4 * 32, 0, st>>>(s->seg_off, s->t, s->flux, s->err, s->trank, ObjClass{s->long_list, s->n_long, MAX_OBS, scratch}, capl, out_dev);
-    cudaError_t e = cudaGetLastError();
+    k_stat<<<gl, 4 * 32, 0, st>>>(s->seg_off, s->t, s->flux, s->err, s->trank, ObjClass{s->long_list, s->n_long, MAX_OBS, scratch}, nullptr, capl, out_dev);
+    e = cudaGetLastError();
     cudaFreeAsync(scratch, st);
     if (e != cudaSuccess) return cuda_fail(e, "k_stat (long objects) launch");
     count_launch();

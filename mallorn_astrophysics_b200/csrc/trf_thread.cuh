@@ -23,25 +23,30 @@ struct SmallFactor {            // R0: upper triangular, column-major r[c*NP + k
   double q[NP];
   MLRN_FN void clear() { for (int i = 0; i < NP * NP; ++i) r[i] = 0.0; for (int i = 0; i < NP; ++i) q[i] = 0.0; }
   // fold the row (v, rhs) in; v is destroyed
-  MLRN_NOINLINE void add_row(double* v, double rhs) {
+  MLRN_NOINLINE void add_row(double* v, double rhs) { fold(v, rhs); }
+  // The same, inlined at the call site: with a factor that is a local object of the caller every index is a compile-time
+  // constant and the 15 + NP live values stay in registers across the row loop (jacobian_pass).  The multiply-adds are
+  // written out as fma() so that the rounding does not depend on the context the compiler contracts them in (inlined
+  // and out of line, device and host give the same bits).
+  MLRN_FN_FORCE void fold(double* v, double rhs) {
 #pragma unroll
     for (int c = 0; c < NP; ++c) {
       const double b = v[c];
       if (b != 0.0) {
         const double a = r[c * NP + c];
-        const double h2 = a * a + b * b;
+        const double h2 = fma(a, a, b * b);
         const double rh = rsqrt(h2);                 // one MUFU + Newton step instead of sqrt and two divisions
         const double cs = a * rh, sn = b * rh;
         r[c * NP + c] = h2 * rh;
 #pragma unroll
         for (int k = c + 1; k < NP; ++k) {
           const double rk = r[k * NP + c], vk = v[k];
-          r[k * NP + c] = cs * rk + sn * vk;
-          v[k] = cs * vk - sn * rk;
+          r[k * NP + c] = fma(cs, rk, sn * vk);
+          v[k] = fma(cs, vk, -(sn * rk));
         }
         const double qc = q[c];
-        q[c] = cs * qc + sn * rhs;
-        rhs = cs * rhs - sn * qc;
+        q[c] = fma(cs, qc, sn * rhs);
+        rhs = fma(cs, rhs, -(sn * qc));
       }
     }
   }
@@ -80,7 +85,8 @@ struct TrfThread {
   SmallFactor<NP> F0;                 // factor of the unscaled Jacobian at x
   double d[NP], diag_h[NP], g_h[NP], sv[NP], V[NP * NP], uf[NP], theta, g_norm;
   int nfev, status;
-  bool need_jac;
+  int pending;                        // final status whose closing Jacobian pass is still to run (-1: none)
+  bool need_jac, jac_ok;              // jac_ok: outcome of the pass jacobian_warp() ran for this trip
 
   MLRN_NOINLINE double residual_cost(const double* xx, bool& finite) const {
     double acc = 0.0; bool bad = false;
@@ -131,13 +137,14 @@ struct TrfThread {
     cost = residual_cost(x, finite);
     nfev = 1;
     if (!finite) return TRF_F0_NONFINITE;
-    need_jac = true; alpha = 0.0; Delta = -1.0;     // Delta < 0: initialise after the first gradient
+    need_jac = true; jac_ok = false; pending = -1; alpha = 0.0; Delta = -1.0;     // Delta < 0: initialise after the first gradient
     return TRF_RUNNING;
   }
 
   // residual + forward-difference Jacobian at x, streamed into F0; g = J^T f
-  MLRN_NOINLINE bool jacobian_pass() {
-    double xpd[NP], dx[NP];                 // perturbed value of parameter c, and the exactly representable step
+  // forward-difference steps at x (scipy approx_derivative, '2-point' with bounds): the perturbed value of parameter c and
+  // the exactly representable step
+  MLRN_FN void perturbation(double* xpd, double* dx) const {
     for (int c = 0; c < NP; ++c) {
       const double sgn = (x[c] >= 0.0) ? 1.0 : -1.0;
       double h = TRF_SQRT_EPS * sgn * fmax(1.0, fabs(x[c]));
@@ -150,7 +157,115 @@ struct TrfThread {
       xpd[c] = x[c] + h;
       dx[c] = xpd[c] - x[c];
     }
-    F0.clear();
+  }
+  MLRN_FN void store_factor(const SmallFactor<NP>& F) {
+#pragma unroll
+    for (int c = 0; c < NP; ++c) {
+#pragma unroll
+      for (int k = 0; k < NP; ++k) F0.r[c * NP + k] = (k <= c) ? F.r[c * NP + k] : 0.0;
+      F0.q[c] = F.q[c];
+    }
+  }
+  MLRN_FN void gradient() {
+#pragma unroll
+    for (int c = 0; c < NP; ++c) { double a = 0.0; for (int k = 0; k <= c; ++k) a += F0.r[c * NP + k] * F0.q[k]; g[c] = a; }
+  }
+
+#ifdef __CUDA_ARCH__
+  template <class T>
+  static __device__ __forceinline__ T shfl_any(const T& v, int src) {
+    static_assert(sizeof(T) % 4 == 0, "shuffled in 32-bit words");
+    T out;
+    const unsigned* a = reinterpret_cast<const unsigned*>(&v);
+    unsigned* b = reinterpret_cast<unsigned*>(&out);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 4); ++i) b[i] = __shfl_sync(0xffffffffu, a[i], src);
+    return out;
+  }
+  // LANE LENDING (thread mode).  A Jacobian pass is six model evaluations per row and only follows an ACCEPTED step, so at
+  // any trip about half the lanes of a warp have none to do (ncu: 11.6 of 32 threads active in the model-evaluation code,
+  // which is over half of all instructions).  Called by ALL 32 lanes of a converged warp before step(): every lane without
+  // a pass of its own (`want` false: a rejected step, no fit at all) is paired with a lane that has one and evaluates the
+  // odd rows of that fit -- the owner's x, steps and model travel by shuffle, the rows come back by shuffle -- while the
+  // owner evaluates the even rows and folds both, in row order, into its factor.  Same operations on the same operands
+  // in the same order: the result is bit-identical to jacobian_pass().  Sets jac_ok.
+  __device__ __noinline__ void jacobian_warp(bool want) {
+    const unsigned FULLM = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned busy = __ballot_sync(FULLM, want);
+    if (busy == 0u) return;
+    const unsigned idle = ~busy, below = (1u << lane) - 1u;
+    const unsigned own = want ? busy : idle, other = want ? idle : busy;
+    const int rank = __popc(own & below);
+    const int partner = (rank < __popc(other)) ? (int)__fns(other, 0, rank + 1) : -1;
+    const bool paired = partner >= 0;
+    const int src = (want || !paired) ? lane : partner;      // the lane whose fit this lane evaluates rows of
+    double xo[NP], xpd[NP], dx[NP];
+#pragma unroll
+    for (int c = 0; c < NP; ++c) { xo[c] = 0.0; xpd[c] = 0.0; dx[c] = 1.0; }
+    if (want) {
+      perturbation(xpd, dx);
+#pragma unroll
+      for (int c = 0; c < NP; ++c) xo[c] = x[c];
+    }
+#pragma unroll
+    for (int c = 0; c < NP; ++c) { xo[c] = __shfl_sync(FULLM, xo[c], src); xpd[c] = __shfl_sync(FULLM, xpd[c], src); dx[c] = __shfl_sync(FULLM, dx[c], src); }
+    const Model mo = shfl_any(mdl, src);
+    const int rows = __shfl_sync(FULLM, want ? m : 0, src);
+    const int stride = paired ? 2 : 1, first = (!want && paired) ? 1 : 0;
+    const int my_trips = (want || paired) ? (rows - first + stride - 1) / stride : 0;
+    const int trips = __reduce_max_sync(FULLM, my_trips > 0 ? my_trips : 0);
+    SmallFactor<NP> F;
+    F.clear();
+    bool bad = false;
+#pragma unroll 1
+    for (int j = 0; j < trips; ++j) {
+      const int i = first + j * stride;
+      double row[NP], r0 = 0.0;
+#pragma unroll
+      for (int c = 0; c < NP; ++c) row[c] = 0.0;
+      const bool mine = (want || paired) && i < rows;
+      if (mine) r0 = mo.fd_row(i, xo, xpd, dx, row);
+      const int from = (want && paired) ? partner : lane;
+      double hrow[NP];
+#pragma unroll
+      for (int c = 0; c < NP; ++c) hrow[c] = __shfl_sync(FULLM, row[c], from);
+      const double hr0 = __shfl_sync(FULLM, r0, from);
+      if (want) {
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {                  // row i, then the helper's row i + 1 (one copy of the fold)
+          if (h == 0 ? mine : (paired && i + 1 < rows)) {
+            double v[NP];
+#pragma unroll
+            for (int c = 0; c < NP; ++c) { v[c] = h ? hrow[c] : row[c]; bad = bad || !is_finite(v[c]); }
+            F.fold(v, h ? hr0 : r0);
+          }
+        }
+      }
+    }
+    if (want) {
+      store_factor(F);
+      jac_ok = !bad;
+      if (!bad) gradient();
+    }
+  }
+#endif
+
+  MLRN_NOINLINE bool jacobian_pass() {
+    double xpd[NP], dx[NP];
+    perturbation(xpd, dx);
+#if !defined(TRF_LOCAL_FACTOR) && defined(__CUDA_ARCH__)
+    // The factor lives in registers while the rows stream in (the noinline add_row pinned it in local memory: 40 local
+    // loads/stores per row, most of the pass's memory traffic: Bazin 282 k -> 391 k objects/s at 10^6 objects together with
+    // the work order of fits.cu); stored to the solver state once, after the last row.
+    SmallFactor<NP> F;
+    F.clear();
+#define TRF_FOLD(row, rhs) F.fold(row, rhs)
+#else
+    SmallFactor<NP>& F = F0;
+    F.clear();
+#define TRF_FOLD(row, rhs) F.add_row(row, rhs)
+#endif
     bool bad = false;
 #ifdef __CUDA_ARCH__
     if (COOP) {
@@ -166,7 +281,7 @@ struct TrfThread {
           double row[NP];
 #pragma unroll
           for (int c = 0; c < NP; ++c) { row[c] = __shfl_sync(0xffffffffu, mine[c], j); bad = bad || !is_finite(row[c]); }
-          F0.add_row(row, __shfl_sync(0xffffffffu, r_mine, j));
+          TRF_FOLD(row, __shfl_sync(0xffffffffu, r_mine, j));
         }
       }
     } else
@@ -176,11 +291,14 @@ struct TrfThread {
       const double r0 = mdl.fd_row(i, x, xpd, dx, row);
 #pragma unroll
       for (int c = 0; c < NP; ++c) bad = bad || !is_finite(row[c]);
-      F0.add_row(row, r0);
+      TRF_FOLD(row, r0);
     }
+#undef TRF_FOLD
+#if !defined(TRF_LOCAL_FACTOR) && defined(__CUDA_ARCH__)
+    store_factor(F);
+#endif
     if (bad) return false;
-#pragma unroll
-    for (int c = 0; c < NP; ++c) { double a = 0.0; for (int k = 0; k <= c; ++k) a += F0.r[c * NP + k] * F0.q[k]; g[c] = a; }
+    gradient();
     return true;
   }
 
@@ -189,7 +307,13 @@ struct TrfThread {
     const double ftol = 1e-8, xtol = 1e-8, gtol = 1e-8;
     double v[NP], dv[NP];
     if (need_jac) {
-      if (!jacobian_pass()) return TRF_J_NONFINITE;
+#if defined(__CUDA_ARCH__) && !defined(TRF_NO_LEND)
+      const bool ok = COOP ? jacobian_pass() : jac_ok;       // thread mode: jacobian_warp() ran it for this trip
+#else
+      const bool ok = jacobian_pass();
+#endif
+      if (!ok) return TRF_J_NONFINITE;
+      if (pending != -1) return pending;            // that was the closing pass of a fit that had converged
       cl_scaling<NP>(x, g, lb, ub, v, dv);
       if (Delta < 0.0) {
         double a = 0.0; for (int i = 0; i < NP; ++i) { const double q = x[i] / sqrt(v[i]); a += q * q; }
@@ -300,8 +424,9 @@ struct TrfThread {
       need_jac = true;
       if (term != -1) {
         // SciPy evaluates the Jacobian at the accepted point before it returns; curve_fit then takes its SVD
-        // and raises on a non-finite entry
-        if (!jacobian_pass()) return TRF_J_NONFINITE;
+        // and raises on a non-finite entry: the next trip runs that pass (with every other pass of the warp) and returns
+        pending = term;
+        return TRF_RUNNING;
       }
     }
     if (term != -1) return term;
