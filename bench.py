@@ -469,7 +469,7 @@ def run_gpu_arm(args):
         if stat_ms:
             ach = algorithmic_bytes(n_rows, n_obj) / (stat_ms * 1e-3) / 1e9
             per_obj = NCU.get("stat_dram_bytes_per_object")
-            roof = {"kernel": "k_stat (moment pass, stat_fast.cu)", "bound": "hbm", "achieved": ach, "peak": peak,
+            roof = {"kernel": "k_stat_warp (moment pass, stat_warp.cuh / stat_fast.cu)", "bound": "hbm", "achieved": ach, "peak": peak,
                     "unit": "GB/s", "frac": ach / peak,
                     "traffic": per_obj * n_obj if per_obj else None,
                     "traffic_source": NCU.get("stat_source"),

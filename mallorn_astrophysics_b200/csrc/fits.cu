@@ -191,7 +191,6 @@ __global__ void __launch_bounds__(FIT_THREADS, FIT_MIN_BLOCKS) k_fit_stage(P pol
     total = pol.total();
   }
   Job job;
-  job.trf.need_jac = false;
   bool active = false, exhausted = !COOP && lane >= lanes, may_export = outc != nullptr;
   long long fit = 0;
   for (;;) {
@@ -218,9 +217,6 @@ __global__ void __launch_bounds__(FIT_THREADS, FIT_MIN_BLOCKS) k_fit_stage(P pol
         if (n_jac > 0) atomicAdd(&g_fit_stats[7], 1ULL);
       }
     }
-#endif
-#ifndef TRF_NO_LEND
-    if (!COOP) job.trf.jacobian_warp(active && job.trf.need_jac);      // every lane: those without a pass of their own lend a hand
 #endif
     if (active) {
       const int rc = job.step();                      // COOP: every lane advances the same fit (uniform control flow)

@@ -303,7 +303,7 @@ k_stat(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
 // values -- goes on `fb_list` for k_stat above; objects beyond SHORT_LIMIT are the long-object launch's.
 constexpr int SW_WARPS = 4;
 #ifndef SW_MIN_BLOCKS
-#define SW_MIN_BLOCKS 4
+#define SW_MIN_BLOCKS 5
 #endif
 __global__ void __launch_bounds__(SW_WARPS * 32, SW_MIN_BLOCKS)
 k_stat_warp(const long long* __restrict__ seg_off, const double* __restrict__ gt, const double* __restrict__ gf,

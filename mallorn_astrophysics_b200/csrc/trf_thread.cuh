@@ -85,8 +85,7 @@ struct TrfThread {
   SmallFactor<NP> F0;                 // factor of the unscaled Jacobian at x
   double d[NP], diag_h[NP], g_h[NP], sv[NP], V[NP * NP], uf[NP], theta, g_norm;
   int nfev, status;
-  int pending;                        // final status whose closing Jacobian pass is still to run (-1: none)
-  bool need_jac, jac_ok;              // jac_ok: outcome of the pass jacobian_warp() ran for this trip
+  bool need_jac;
 
   MLRN_NOINLINE double residual_cost(const double* xx, bool& finite) const {
     double acc = 0.0; bool bad = false;
@@ -137,7 +136,7 @@ struct TrfThread {
     cost = residual_cost(x, finite);
     nfev = 1;
     if (!finite) return TRF_F0_NONFINITE;
-    need_jac = true; jac_ok = false; pending = -1; alpha = 0.0; Delta = -1.0;     // Delta < 0: initialise after the first gradient
+    need_jac = true; alpha = 0.0; Delta = -1.0;     // Delta < 0: initialise after the first gradient
     return TRF_RUNNING;
   }
 
@@ -170,86 +169,6 @@ struct TrfThread {
 #pragma unroll
     for (int c = 0; c < NP; ++c) { double a = 0.0; for (int k = 0; k <= c; ++k) a += F0.r[c * NP + k] * F0.q[k]; g[c] = a; }
   }
-
-#ifdef __CUDA_ARCH__
-  template <class T>
-  static __device__ __forceinline__ T shfl_any(const T& v, int src) {
-    static_assert(sizeof(T) % 4 == 0, "shuffled in 32-bit words");
-    T out;
-    const unsigned* a = reinterpret_cast<const unsigned*>(&v);
-    unsigned* b = reinterpret_cast<unsigned*>(&out);
-#pragma unroll
-    for (int i = 0; i < (int)(sizeof(T) / 4); ++i) b[i] = __shfl_sync(0xffffffffu, a[i], src);
-    return out;
-  }
-  // LANE LENDING (thread mode).  A Jacobian pass is six model evaluations per row and only follows an ACCEPTED step, so at
-  // any trip about half the lanes of a warp have none to do (ncu: 11.6 of 32 threads active in the model-evaluation code,
-  // which is over half of all instructions).  Called by ALL 32 lanes of a converged warp before step(): every lane without
-  // a pass of its own (`want` false: a rejected step, no fit at all) is paired with a lane that has one and evaluates the
-  // odd rows of that fit -- the owner's x, steps and model travel by shuffle, the rows come back by shuffle -- while the
-  // owner evaluates the even rows and folds both, in row order, into its factor.  Same operations on the same operands
-  // in the same order: the result is bit-identical to jacobian_pass().  Sets jac_ok.
-  __device__ __noinline__ void jacobian_warp(bool want) {
-    const unsigned FULLM = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const unsigned busy = __ballot_sync(FULLM, want);
-    if (busy == 0u) return;
-    const unsigned idle = ~busy, below = (1u << lane) - 1u;
-    const unsigned own = want ? busy : idle, other = want ? idle : busy;
-    const int rank = __popc(own & below);
-    const int partner = (rank < __popc(other)) ? (int)__fns(other, 0, rank + 1) : -1;
-    const bool paired = partner >= 0;
-    const int src = (want || !paired) ? lane : partner;      // the lane whose fit this lane evaluates rows of
-    double xo[NP], xpd[NP], dx[NP];
-#pragma unroll
-    for (int c = 0; c < NP; ++c) { xo[c] = 0.0; xpd[c] = 0.0; dx[c] = 1.0; }
-    if (want) {
-      perturbation(xpd, dx);
-#pragma unroll
-      for (int c = 0; c < NP; ++c) xo[c] = x[c];
-    }
-#pragma unroll
-    for (int c = 0; c < NP; ++c) { xo[c] = __shfl_sync(FULLM, xo[c], src); xpd[c] = __shfl_sync(FULLM, xpd[c], src); dx[c] = __shfl_sync(FULLM, dx[c], src); }
-    const Model mo = shfl_any(mdl, src);
-    const int rows = __shfl_sync(FULLM, want ? m : 0, src);
-    const int stride = paired ? 2 : 1, first = (!want && paired) ? 1 : 0;
-    const int my_trips = (want || paired) ? (rows - first + stride - 1) / stride : 0;
-    const int trips = __reduce_max_sync(FULLM, my_trips > 0 ? my_trips : 0);
-    SmallFactor<NP> F;
-    F.clear();
-    bool bad = false;
-#pragma unroll 1
-    for (int j = 0; j < trips; ++j) {
-      const int i = first + j * stride;
-      double row[NP], r0 = 0.0;
-#pragma unroll
-      for (int c = 0; c < NP; ++c) row[c] = 0.0;
-      const bool mine = (want || paired) && i < rows;
-      if (mine) r0 = mo.fd_row(i, xo, xpd, dx, row);
-      const int from = (want && paired) ? partner : lane;
-      double hrow[NP];
-#pragma unroll
-      for (int c = 0; c < NP; ++c) hrow[c] = __shfl_sync(FULLM, row[c], from);
-      const double hr0 = __shfl_sync(FULLM, r0, from);
-      if (want) {
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {                  // row i, then the helper's row i + 1 (one copy of the fold)
-          if (h == 0 ? mine : (paired && i + 1 < rows)) {
-            double v[NP];
-#pragma unroll
-            for (int c = 0; c < NP; ++c) { v[c] = h ? hrow[c] : row[c]; bad = bad || !is_finite(v[c]); }
-            F.fold(v, h ? hr0 : r0);
-          }
-        }
-      }
-    }
-    if (want) {
-      store_factor(F);
-      jac_ok = !bad;
-      if (!bad) gradient();
-    }
-  }
-#endif
 
   MLRN_NOINLINE bool jacobian_pass() {
     double xpd[NP], dx[NP];
@@ -307,13 +226,7 @@ struct TrfThread {
     const double ftol = 1e-8, xtol = 1e-8, gtol = 1e-8;
     double v[NP], dv[NP];
     if (need_jac) {
-#if defined(__CUDA_ARCH__) && !defined(TRF_NO_LEND)
-      const bool ok = COOP ? jacobian_pass() : jac_ok;       // thread mode: jacobian_warp() ran it for this trip
-#else
-      const bool ok = jacobian_pass();
-#endif
-      if (!ok) return TRF_J_NONFINITE;
-      if (pending != -1) return pending;            // that was the closing pass of a fit that had converged
+      if (!jacobian_pass()) return TRF_J_NONFINITE;
       cl_scaling<NP>(x, g, lb, ub, v, dv);
       if (Delta < 0.0) {
         double a = 0.0; for (int i = 0; i < NP; ++i) { const double q = x[i] / sqrt(v[i]); a += q * q; }
@@ -424,9 +337,8 @@ struct TrfThread {
       need_jac = true;
       if (term != -1) {
         // SciPy evaluates the Jacobian at the accepted point before it returns; curve_fit then takes its SVD
-        // and raises on a non-finite entry: the next trip runs that pass (with every other pass of the warp) and returns
-        pending = term;
-        return TRF_RUNNING;
+        // and raises on a non-finite entry
+        if (!jacobian_pass()) return TRF_J_NONFINITE;
       }
     }
     if (term != -1) return term;

@@ -242,3 +242,42 @@ def test_long_objects_up_to_the_cap():
             present, want = run_table(m, table)
             _compare(got[m][present], want, rtol=1e-5, atol=1e-9, what=f"{m}/long")
     assert np.isfinite(got["gp2d"][:, 0]).all() and np.isfinite(got["bazin"][:, 8 * 2]).any()
+
+
+def test_statistical_fast_path_corner_cases():
+    """stat_warp.cuh: 24-bit key ties repaired on the exact values (a huge outlier squeezes every other flux of the object into
+    a handful of keys, in reversed order), 255 observations (last object of the fast path) next to 256 (first of the general
+    kernel), constant fluxes, one- and two-point bands, an unknown-filter segment: all against the oracle."""
+    from mallorn_astrophysics_b200.store import LightCurveStore
+    from mallorn_astrophysics_b200.synth import LightCurveTable
+    from oracle.extract import run_table
+    rng = np.random.default_rng(11)
+    obj, band, t, f, e = [], [], [], [], []
+
+    def add(o, n, flux, bands=None, times=None):
+        obj.append(np.full(n, o)); f.append(np.asarray(flux, dtype=float))
+        band.append(rng.integers(0, 6, n) if bands is None else np.asarray(bands))
+        t.append(59000.0 + np.sort(rng.uniform(0.0, 900.0, n)) if times is None else np.asarray(times, dtype=float))
+        e.append(rng.uniform(0.5, 2.0, n))
+
+    add(0, 200, np.concatenate([1000.0 - 1e-6 * np.arange(199), [1e9]]))             # ties, reversed order, one outlier
+    add(1, 255, rng.normal(50.0, 5.0, 255))
+    add(2, 256, rng.normal(50.0, 5.0, 256))
+    add(3, 120, np.full(120, 3.25))                                                    # constant
+    add(4, 1, [7.0], bands=[2])
+    add(5, 12, rng.normal(0.0, 1.0, 12), bands=[0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5])   # two points per band
+    add(6, 90, rng.normal(-3.0, 1.0, 90), bands=rng.integers(0, 7, 90))               # with unknown-filter rows
+    add(7, 64, np.repeat(rng.normal(10.0, 2.0, 8), 8), bands=np.tile(np.arange(4), 16))   # exact duplicates
+    add(8, 150, rng.normal(1e-3, 1e-6, 150) + np.where(np.arange(150) == 77, 5e3, 0.0))  # outlier, ordinary order
+    n_obj = 9
+    o = np.concatenate(obj).astype(np.int32)
+    perm = rng.permutation(len(o))                                                       # file order is not object order
+    cols = [np.concatenate(x)[perm] for x in (obj, band, t, f, e)]
+    table = LightCurveTable(cols[0].astype(np.int32), cols[1].astype(np.uint8), cols[2], cols[3], cols[4], n_obj,
+                            np.zeros(n_obj), np.zeros(n_obj), np.zeros(n_obj, np.int64), "corners")
+    with LightCurveStore.from_table(table) as s:
+        got = s.features("statistical")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        present, want = run_table("statistical", table)
+    _compare(got[present], want, rtol=1e-5, atol=1e-9, what="statistical/corner cases")
