@@ -477,7 +477,7 @@ def run_gpu_arm(args):
                     "algorithmic_bytes_per_launch": algorithmic_bytes(n_rows, n_obj), "ms_per_launch": stat_ms}
         roof_gp = None
         if gp_status is not None and pass_ms.get("gp2d"):
-            # dominant kernel of the step: FP64 work of the GP = (evaluations + the one at the optimum) x N^3 flop
+            # dominant kernel of the step: FP64 work of the GP = evaluations x N^3 flop
             # (N^3/2 FMA per -lnL + gradient evaluation) over its CUDA-event time, against the FP64
             # rate measured on this device right now (the DMMA loop: the instruction the sweep issues)
             dfma, dmma = ctypes.c_double(0.0), ctypes.c_double(0.0)
@@ -485,7 +485,7 @@ def run_gpu_arm(args):
             fp64_peak = max(dfma.value, dmma.value) if rc == 0 and max(dfma.value, dmma.value) > 0 else 37.1
             stt = gp_status.to(torch.float64)
             fitted = stt[:, 3] >= 10
-            flop = float((((stt[:, 1] + 1.0) * stt[:, 3] ** 3)[fitted]).sum())
+            flop = float(((stt[:, 1] * stt[:, 3] ** 3)[fitted]).sum())      # nfev evaluations (the one at the optimum is normally not repeated)
             gp_ms = pass_ms["gp2d"] / args.steps
             ach_tf = flop / (gp_ms * 1e-3) / 1e12
             roof_gp = {"kernel": "k_gp2d (2-D GP)", "bound": "tensor", "achieved": ach_tf, "peak": fp64_peak,

@@ -51,8 +51,14 @@ struct BazinJobT {
     const double* x = trf.x;
     const double A = clip(x[0], -1e6, 1e6), tr = clip(x[2], 0.1, 1e4), tf = clip(x[3], 0.1, 1e4), B = clip(x[4], -1e6, 1e6);
     const double xc[5] = {A, x[1], tr, tf, B};
-    double chi = 0.0;
-    for (int i = 0; i < n; ++i) { const double sg = (e[i] > 0.0) ? e[i] : 1.0; const double r = (f[i] - bazin_value(t[i], xc)) / sg; chi += r * r; }
+    // chi^2 of the clipped curve (:160-166).  The clips are inactive for any fit inside its bounds with |A|, |B| <= 1e6,
+    // and then the sum is the solver's own final cost (0.5 sum r^2 over the same rows, r = (model - f) / sigma): no second
+    // pass over the band by a single lane of the warp
+    double chi = 2.0 * trf.cost;
+    if (!(A == x[0] && tr == x[2] && tf == x[3] && B == x[4])) {
+      chi = 0.0;
+      for (int i = 0; i < n; ++i) { const double sg = (e[i] > 0.0) ? e[i] : 1.0; const double r = (f[i] - bazin_value(t[i], xc)) / sg; chi += r * r; }
+    }
     out[0] = A; out[1] = x[1]; out[2] = tr; out[3] = tf; out[4] = B;
     out[5] = clip(chi / (double)(n - 5), 0.0, 1e6);
     out[6] = clip(tr / (tf + 1e-6), 0.0, 100.0);
@@ -63,23 +69,37 @@ struct BazinJobT {
 using BazinJob = BazinJobT<false>;
 
 // decline models on the post-peak suffix of a time-sorted band: x_i = t_i - t_peak, y_i = f_i
+struct NoPrep {};
 struct PowerModelT {
   const double* t; const double* y; double pt, k;
-  MLRN_FN double fd_row(int i, const double* x, const double* xpd, const double* dx, double* row) const { return generic_fd_row<2>(*this, i, x, xpd, dx, row); }
-  MLRN_FN_FORCE double value(int i, const double* p) const { return p[0] * pow(fmax((t[i] - pt) - p[1], 0.1), k); }
-  MLRN_FN_FORCE double resid(int i, const double* p) const { return value(i, p) - y[i]; }
+  using Prep1 = NoPrep; using Prep = GenericPrep<2, PowerModelT>;
+  MLRN_FN_FORCE Prep1 prepare1(const double*) const { return Prep1{}; }
+  MLRN_FN_FORCE Prep prepare(const double* x, const double* xpd) const { return generic_prepare<2>(*this, x, xpd); }
+  MLRN_FN double fd_row(int i, const double* x, const double* xpd, const double* dx, const double* rdx, const Prep& p, double* row) const { return generic_fd_row<2>(*this, i, x, xpd, dx, rdx, p, row); }
+  // x^k as exp(k ln x): the base is clipped to >= 0.1, so none of pow()'s special cases can occur and the general routine
+  // (about twice the instructions) is not needed; |k ln x| <= 3 * 12, i.e. the result is good to ~2e-15 relative, far inside
+  // what a two-parameter R^2 can see (asserted at 1e-3)
+  MLRN_FN_FORCE double value(int i, const double* p) const { return p[0] * exp(k * log(fmax((t[i] - pt) - p[1], 0.1))); }
+  MLRN_FN_FORCE double resid(int i, const double* p, const Prep1&) const { return value(i, p) - y[i]; }
 };
 struct ExpModelT {
   const double* t; const double* y; double pt, k;
-  MLRN_FN double fd_row(int i, const double* x, const double* xpd, const double* dx, double* row) const { return generic_fd_row<3>(*this, i, x, xpd, dx, row); }
+  struct Prep1 { double r1; };                            // 1 / tau
+  using Prep = GenericPrep<3, ExpModelT>;
+  MLRN_FN_FORCE Prep1 prepare1(const double* p) const { Prep1 q; q.r1 = 1.0 / p[1]; return q; }
+  MLRN_FN_FORCE Prep prepare(const double* x, const double* xpd) const { return generic_prepare<3>(*this, x, xpd); }
+  MLRN_FN double fd_row(int i, const double* x, const double* xpd, const double* dx, const double* rdx, const Prep& p, double* row) const { return generic_fd_row<3>(*this, i, x, xpd, dx, rdx, p, row); }
   MLRN_FN_FORCE double value(int i, const double* p) const { return p[0] * exp(-fmax((t[i] - pt) - p[2], 0.0) / p[1]); }
-  MLRN_FN_FORCE double resid(int i, const double* p) const { return value(i, p) - y[i]; }
+  MLRN_FN_FORCE double resid(int i, const double* p, const Prep1& q) const { return p[0] * exp(div_r(-fmax((t[i] - pt) - p[2], 0.0), p[1], q.r1)) - y[i]; }
 };
 struct LinModelT {
   const double* t; const double* y; double pt, k;
-  MLRN_FN double fd_row(int i, const double* x, const double* xpd, const double* dx, double* row) const { return generic_fd_row<3>(*this, i, x, xpd, dx, row); }
+  using Prep1 = NoPrep; using Prep = GenericPrep<3, LinModelT>;
+  MLRN_FN_FORCE Prep1 prepare1(const double*) const { return Prep1{}; }
+  MLRN_FN_FORCE Prep prepare(const double* x, const double* xpd) const { return generic_prepare<3>(*this, x, xpd); }
+  MLRN_FN double fd_row(int i, const double* x, const double* xpd, const double* dx, const double* rdx, const Prep& p, double* row) const { return generic_fd_row<3>(*this, i, x, xpd, dx, rdx, p, row); }
   MLRN_FN_FORCE double value(int i, const double* p) const { return p[0] - p[1] * fmax((t[i] - pt) - p[2], 0.0); }
-  MLRN_FN_FORCE double resid(int i, const double* p) const { return value(i, p) - y[i]; }
+  MLRN_FN_FORCE double resid(int i, const double* p, const Prep1&) const { return value(i, p) - y[i]; }
 };
 
 // KIND 0: power law with fixed index k (NP = 2); 1: exponential (NP = 3); 2: linear (NP = 3)
@@ -122,8 +142,7 @@ struct DeclineJobT {
   MLRN_FN int step() { return trf.step(); }
   MLRN_FN double finish(int status) const {
     if (status <= 0) return qnan();
-    double ss = 0.0;
-    for (int i = 0; i < m; ++i) { const double r = mdl.y[i] - mdl.value(i, trf.x); ss += r * r; }
+    const double ss = 2.0 * trf.cost;          // sum (y - model)^2 at the final point: the solver's cost is half of exactly that sum
     return (ss_tot > 0.0) ? 1.0 - ss / ss_tot : 0.0;                           // :186-189
   }
 };

@@ -639,7 +639,13 @@ k_gp2d(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
       if (!searching) { f_fin = f; break; }            // that was the evaluation at the optimum (alpha for predict)
       if (tid == 0) s_go = s_opt.advance(f, g) ? 1 : 0;
       __syncthreads();
-      if (!s_go) searching = 0;
+      if (!s_go) {
+        // The search normally ends at the point it evaluated last (a successful line search): alpha of the optimum is
+        // still in S.sb and the evaluation the reference repeats for predict() would reproduce it bit for bit -- skipped
+        // (one evaluation in twenty).  Only after an abnormal end (x restored to an earlier iterate) is it run.
+        if (s_opt.x[0] == xk[0] && s_opt.x[1] == xk[1] && s_opt.x[2] == xk[2] && s_opt.x[3] == xk[3]) { f_fin = f; break; }
+        searching = 0;
+      }
     }
     const double p[4] = {s_opt.x[0], s_opt.x[1], s_opt.x[2], s_opt.x[3]};
     const double f_opt = s_opt.f;

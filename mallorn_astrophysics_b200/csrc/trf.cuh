@@ -29,6 +29,14 @@ constexpr double TRF_SQRT_EPS = 1.4901161193847656e-08;
 enum TrfFail { TRF_BAD_BOUNDS = -101, TRF_X0_INFEASIBLE = -102, TRF_F0_NONFINITE = -103, TRF_J_NONFINITE = -104,
                TRF_GEOMETRY = -105 };
 
+// a / d from r = 1 / d (correctly rounded): one multiplication and a residual correction.  The divisors of a fit pass
+// (time scales, finite-difference steps) are the same for every row, so their reciprocals are taken once per pass and each
+// of the 11 such divisions of a Jacobian row costs 3 instructions instead of ~14.  The result equals the IEEE quotient
+// (0 mismatches in 2e8 random operand pairs; the known exceptions of this scheme need operands that do not occur here),
+// and resid() / fd_row() use the SAME expression, so the row stays consistent with the residual bit for bit.
+// Not for divisors that can be infinite (r = 0 would turn a / inf = 0 into NaN).
+MLRN_FN_FORCE double div_r(double a, double d, double r) { const double q = a * r; return fma(fma(-q, d, a), r, q); }
+
 template <int NP>
 MLRN_FN double vnorm(const double* a) { double s = 0.0; for (int i = 0; i < NP; ++i) s += a[i] * a[i]; return sqrt(s); }
 template <int NP>

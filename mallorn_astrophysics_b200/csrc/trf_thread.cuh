@@ -54,17 +54,32 @@ struct SmallFactor {            // R0: upper triangular, column-major r[c*NP + k
 
 enum { TRF_RUNNING = 100 };
 
-// forward-difference row of a model without a specialised fd_row: one full evaluation per parameter
+// forward-difference row of a model without a specialised fd_row: one full evaluation per parameter.  The per-vector
+// preparations of the model (reciprocals of its divisors, Model::Prep1) are taken once per pass for x and for each of the
+// NP perturbed vectors.
+template <int NP, class Model> struct GenericPrep { typename Model::Prep1 base, pert[NP]; };
 template <int NP, class Model>
-MLRN_FN double generic_fd_row(const Model& mdl, int i, const double* x, const double* xpd, const double* dx, double* row) {
-  const double r0 = mdl.resid(i, x);
+MLRN_FN GenericPrep<NP, Model> generic_prepare(const Model& mdl, const double* x, const double* xpd) {
+  GenericPrep<NP, Model> g;
+  g.base = mdl.prepare1(x);
+  double xp[NP];
+#pragma unroll
+  for (int k = 0; k < NP; ++k) xp[k] = x[k];
+#pragma unroll
+  for (int c = 0; c < NP; ++c) { xp[c] = xpd[c]; g.pert[c] = mdl.prepare1(xp); xp[c] = x[c]; }
+  return g;
+}
+template <int NP, class Model>
+MLRN_FN double generic_fd_row(const Model& mdl, int i, const double* x, const double* xpd, const double* dx, const double* rdx,
+                              const GenericPrep<NP, Model>& p, double* row) {
+  const double r0 = mdl.resid(i, x, p.base);
   double xp[NP];
 #pragma unroll
   for (int k = 0; k < NP; ++k) xp[k] = x[k];
 #pragma unroll
   for (int c = 0; c < NP; ++c) {
     xp[c] = xpd[c];
-    row[c] = (mdl.resid(i, xp) - r0) / dx[c];
+    row[c] = div_r(mdl.resid(i, xp, p.pert[c]) - r0, dx[c], rdx[c]);
     xp[c] = x[c];
   }
   return r0;
@@ -89,12 +104,13 @@ struct TrfThread {
 
   MLRN_NOINLINE double residual_cost(const double* xx, bool& finite) const {
     double acc = 0.0; bool bad = false;
+    const typename Model::Prep1 pr = mdl.prepare1(xx);
 #ifdef __CUDA_ARCH__
     if (COOP) {
       const int lane = threadIdx.x & 31;
       for (int base = 0; base < m; base += 32) {
         const int i = base + lane;
-        const double mine = (i < m) ? mdl.resid(i, xx) : 0.0;
+        const double mine = (i < m) ? mdl.resid(i, xx, pr) : 0.0;
         const int cnt = (m - base < 32) ? m - base : 32;
         for (int j = 0; j < cnt; ++j) { const double r = __shfl_sync(0xffffffffu, mine, j); acc += r * r; bad = bad || !is_finite(r); }
       }
@@ -102,7 +118,7 @@ struct TrfThread {
       return 0.5 * acc;
     }
 #endif
-    for (int i = 0; i < m; ++i) { const double r = mdl.resid(i, xx); acc += r * r; bad = bad || !is_finite(r); }
+    for (int i = 0; i < m; ++i) { const double r = mdl.resid(i, xx, pr); acc += r * r; bad = bad || !is_finite(r); }
     finite = !bad;
     return 0.5 * acc;
   }
@@ -171,8 +187,10 @@ struct TrfThread {
   }
 
   MLRN_NOINLINE bool jacobian_pass() {
-    double xpd[NP], dx[NP];
+    double xpd[NP], dx[NP], rdx[NP];
     perturbation(xpd, dx);
+    for (int c = 0; c < NP; ++c) rdx[c] = 1.0 / dx[c];          // the steps are the same for every row: see div_r (fits.cuh)
+    const typename Model::Prep prep = mdl.prepare(x, xpd);
 #if !defined(TRF_LOCAL_FACTOR) && defined(__CUDA_ARCH__)
     // The factor lives in registers while the rows stream in (the noinline add_row pinned it in local memory: 40 local
     // loads/stores per row, most of the pass's memory traffic: Bazin 282 k -> 391 k objects/s at 10^6 objects together with
@@ -194,7 +212,7 @@ struct TrfThread {
         double mine[NP], r_mine = 0.0;
 #pragma unroll
         for (int c = 0; c < NP; ++c) mine[c] = 0.0;
-        if (i < m) r_mine = mdl.fd_row(i, x, xpd, dx, mine);
+        if (i < m) r_mine = mdl.fd_row(i, x, xpd, dx, rdx, prep, mine);
         const int cnt = (m - base < 32) ? m - base : 32;
         for (int j = 0; j < cnt; ++j) {
           double row[NP];
@@ -207,7 +225,7 @@ struct TrfThread {
 #endif
     for (int i = 0; i < m; ++i) {
       double row[NP];
-      const double r0 = mdl.fd_row(i, x, xpd, dx, row);
+      const double r0 = mdl.fd_row(i, x, xpd, dx, rdx, prep, row);
 #pragma unroll
       for (int c = 0; c < NP; ++c) bad = bad || !is_finite(row[c]);
       TRF_FOLD(row, r0);
