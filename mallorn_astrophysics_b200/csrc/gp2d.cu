@@ -107,13 +107,33 @@ __device__ __forceinline__ KernelPars unpack(const double* p) {
 // The rank-16 update -- 45 of the 63 tile products of a sweep step -- then reads and writes its accumulators as four
 // conflict-free 128-bit accesses per lane; the column-major layout of round 1 cost eight 64-bit accesses with a 2-way
 // bank conflict each, and the sweep is bound by shared-memory bandwidth (8 KB of traffic per 4096-FMA tile product).
+// On top of that, the two halves (columns 0-3 / 4-7 of an 8x8 quadrant) of rows 2, 3, 6, 7 are exchanged (GP_SWZ): rows are
+// 8 doubles = 16 banks apart, so without the exchange rows r and r + 2 of a quadrant fall on the same banks, and every
+// access that walks DOWN a column -- the A-operand fragments of tile_scale, the pivot warp's row loads, the transposed
+// stores of tile_finalise -- was a 4-way bank conflict (ncu: 17.5 % of the kernel's shared-memory wavefronts excessive, all
+// in these three places).  With the exchange the first two are conflict-free and the third is 2-way; the accumulator
+// accesses stay conflict-free (a lane reads its pair at lane ^ ((lane >> 2) & 2), see frag_lane()).
+#ifndef GP_NO_SWZ
+#define GP_SWZ(r) ((((r) >> 1) & 1) << 2)
+#else
+#define GP_SWZ(r) 0
+#endif
 __device__ __forceinline__ int tix(int r, int c) {
-  return ((((r >> 3) * 2 + (c >> 3)) * 32 + (r & 7) * 4 + ((c & 7) >> 1)) << 1) | (c & 1);
+  return ((((r >> 3) * 2 + (c >> 3)) * 32 + (r & 7) * 4 + (((c & 7) ^ GP_SWZ(r)) >> 1)) << 1) | (c & 1);
 }
 // inverse: storage index -> (r, c); consecutive threads then touch consecutive words
 __device__ __forceinline__ void tix_decode(int idx, int& r, int& c) {
   r = ((idx >> 7) << 3) | ((idx >> 3) & 7);
-  c = (((idx >> 6) & 1) << 3) | (((idx >> 1) & 3) << 1) | (idx & 1);
+  c = (((idx >> 6) & 1) << 3) | ((((((idx >> 1) & 3) << 1) | (idx & 1))) ^ GP_SWZ(r));
+}
+// the double2 slot (within a 32-slot quadrant) that holds lane's accumulator pair C[lane/4][2(lane%4) .. +1]
+__device__ __forceinline__ int frag_lane() {
+  const int lane = threadIdx.x & 31;
+#ifndef GP_NO_SWZ
+  return lane ^ ((lane >> 2) & 2);
+#else
+  return lane;
+#endif
 }
 
 // running product of the pivots as mantissa * 2^exponent (ln|K| is taken once per evaluation, off the critical path)
@@ -199,7 +219,7 @@ __device__ __forceinline__ void dmma_16x16x16(double (&acc)[2][2][2], const doub
 
 // C(i, j) -= Vi Vj^T        (C in fragment order, V tiles k-major with stride VLD)
 __device__ __forceinline__ void tile_update(double* __restrict__ C, const double* __restrict__ Vi, const double* __restrict__ Vj) {
-  const int lane = threadIdx.x & 31;
+  const int lane = frag_lane();
   double2* __restrict__ C2 = reinterpret_cast<double2*>(C);
   double acc[2][2][2];
 #pragma unroll
@@ -251,7 +271,7 @@ __device__ __forceinline__ void tile_finalise(double* __restrict__ Tl, bool tran
 #pragma unroll
     for (int ri = 0; ri < 2; ++ri)
 #pragma unroll
-      for (int ci = 0; ci < 2; ++ci) T2[(ri * 2 + ci) * 32 + lane] = make_double2(acc[ri][ci][0], acc[ri][ci][1]);
+      for (int ci = 0; ci < 2; ++ci) T2[(ri * 2 + ci) * 32 + frag_lane()] = make_double2(acc[ri][ci][0], acc[ri][ci][1]);
   } else {
 #pragma unroll
     for (int ri = 0; ri < 2; ++ri)
@@ -412,7 +432,7 @@ __device__ __forceinline__ void gp_eval(const GpShared& S, double* __restrict__ 
 #pragma unroll
         for (int ri = 0; ri < 2; ++ri)
 #pragma unroll
-          for (int ci = 0; ci < 2; ++ci) P2[(ri * 2 + ci) * 32 + lane] = make_double2(-acc[ri][ci][0], -acc[ri][ci][1]);
+          for (int ci = 0; ci < 2; ++ci) P2[(ri * 2 + ci) * 32 + frag_lane()] = make_double2(-acc[ri][ci][0], -acc[ri][ci][1]);
         if (lane < TB) {
           double s = 0.0;
           for (int m = lane; m < TB; ++m) s += Li[m * TB + lane] * wv[m];

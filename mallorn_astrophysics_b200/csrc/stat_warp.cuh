@@ -34,11 +34,10 @@ constexpr int MRG = CAP + CAP / 8;       // merged run, skewed by one slot per 8
 constexpr int ROW = 128;
 
 struct WarpSmem {
-  double st[CAP];          // times, store order (band-major, time-sorted inside a band)
+  double st[CAP];          // times, store order (band-major, time-sorted inside a band); after the group phase: the output row
   double sf[CAP];          // fluxes, store order
   double sa[MRG];          // flat phase: |f|/err or -1; after the sort: all fluxes ascending (skewed index)
   double sb[CAP];          // flat phase: |df/dt| to the next observation of the same band or 0; after the sort: the band runs
-  double row[ROW];
   unsigned char inv[CAP];  // store index of the observation with a given time rank
   unsigned char sband[CAP];
   int soff[8];
@@ -211,6 +210,7 @@ __device__ __forceinline__ bool stat_object(WarpSmem& w, const long long* __rest
   const int gq = lane >> 2, p = lane & 3;
   const int glo = (gq < 7) ? w.soff[gq] : 0;
   const int nb = (gq < 7) ? w.soff[gq + 1] - glo : 0;
+  const double tb0 = (nb > 0) ? w.st[glo] : 0.0, tb1 = (nb > 0) ? w.st[glo + nb - 1] : 0.0;      // the band is time-sorted
   double s1 = 0.0, snr = 0.0, slope = 0.0; int nsnr = 0;
   for (int i = p; i < nb; i += 4) {
     s1 += w.sf[glo + i];
@@ -267,7 +267,10 @@ __device__ __forceinline__ bool stat_object(WarpSmem& w, const long long* __rest
   const bool all = (gq == 7);
   const int nn = all ? n : nb;
   const bool leader = (p == 0) && (gq != 6);
-  double* rw = w.row + (all ? 6 : gq) * N_STAT;
+  static_assert(ROW <= CAP && STAT_COLS <= ROW, "the row is assembled in the storage of the staged times");
+  double* const row = w.st;
+  double* rw = row + (all ? 6 : gq) * N_STAT;
+  __syncwarp();                                            // every lane has read its times: the row takes their place
   if (leader) {
     if (nn == 0) {
       rw[0] = 0.0;
@@ -278,7 +281,7 @@ __device__ __forceinline__ bool stat_object(WarpSmem& w, const long long* __rest
       const double mean = all ? mean_all : mean_b, sd = all ? sd_all : sd_b;
       const double mm3 = all ? M3 : m3, mm4 = all ? M4 : m4;
       const int c1 = all ? B1 : b1, c2 = all ? B2 : b2, ns = all ? NSNR : nsnr;
-      const double tf0 = all ? t_first : w.st[glo], tf1 = all ? t_last : w.st[glo + nb - 1];
+      const double tf0 = all ? t_first : tb0, tf1 = all ? t_last : tb1;
       double skew = 0.0, kurt = 0.0;
       if (sd > 0.0) {
         const double isd = frcp(sd), isd2 = isd * isd;
@@ -389,19 +392,19 @@ __device__ __forceinline__ bool stat_object(WarpSmem& w, const long long* __rest
     const int pa[3] = {BG, BR, BI}, pb[3] = {BR, BI, BZ};
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      const double a = w.row[pa[j] * N_STAT + 1], c = w.row[pb[j] * N_STAT + 1];
-      w.row[k + j] = (!is_nan(a) && c > 0.0) ? a / c : qnan();
+      const double a = row[pa[j] * N_STAT + 1], c = row[pb[j] * N_STAT + 1];
+      row[k + j] = (!is_nan(a) && c > 0.0) ? a / c : qnan();
     }
     int pk = -1; double best = 0.0;
 #pragma unroll
     for (int b = 0; b < N_BAND; ++b) {
-      const double m = w.row[b * N_STAT + 4];
+      const double m = row[b * N_STAT + 4];
       if (!is_nan(m) && (pk < 0 || m > best)) { best = m; pk = b; }
     }
-    w.row[k + 3] = (double)pk;
+    row[k + 3] = (double)pk;
   }
   __syncwarp();
-  for (int c = lane; c < STAT_COLS; c += 32) dst[c] = w.row[c];
+  for (int c = lane; c < STAT_COLS; c += 32) dst[c] = row[c];
   __syncwarp();
   return true;
 }

@@ -34,7 +34,8 @@ def launches(path):
         except ValueError:
             continue
         name = re.sub(r"\(.*", "", r[ki])
-        name = re.sub(r"^.*unnamed>::|^void |mlrn::", "", name)
+        name = re.sub(r"^void ", "", name)
+        name = re.sub(r"(mlrn::)?<?unnamed>::", "", name)          # also inside template arguments (k_fit_stage<BazinPolicyT<0>, 0>)
         a = agg.setdefault(name, [0, 0.0])
         a[0] += 1; a[1] += v
     tot = sum(v for _, v in agg.values())
