@@ -366,7 +366,7 @@ def run_gpu_arm(args):
         stream.synchronize()
         if timed:
             for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
-                pass_ms[name] += a.elapsed_time(b)
+                pass_ms[name] = pass_ms.get(name, 0.0) + a.elapsed_time(b)      # 'bazin+powerlaw': the two fit passes run as one overlapped call (mlrn_fits)
 
     def barrier():
         if world > 1:

@@ -91,6 +91,13 @@ int mlrn_physics(const mlrn_store* s, const double* z, int z_on_device, double* 
 int mlrn_bazin(const mlrn_store* s, double* out, int32_t* status, int out_on_device, void* stream);
 /* status (optional): int32 [n_obj, 27, 2] */
 int mlrn_powerlaw(const mlrn_store* s, double* out, int32_t* status, int out_on_device, void* stream);
+/* Both fit passes of the caching drivers (cache_bazin_features.py:44-60 and the power-law loop of
+ * scripts/train_v55_powerlaw.py:147-202, run one after the other upstream) in ONE call: the Bazin pass is ordered on
+ * `stream`, the decline models on an internal side stream forked from and joined to it, so that the straggler stages of
+ * one pass (a few long fits, most SMs idle) run under the other's bulk.  Same results as mlrn_bazin + mlrn_powerlaw.
+ * Host buffers (out_on_device = 0) are served by the two calls in sequence. */
+int mlrn_fits(const mlrn_store* s, double* bazin_out, int32_t* bazin_status, double* powerlaw_out,
+              int32_t* powerlaw_status, int out_on_device, void* stream);
 /* status (optional): int32 [n_obj, 4] = {L-BFGS-B iterations, function evaluations, termination code, N used} */
 int mlrn_gp2d(const mlrn_store* s, double* out, int32_t* status, int out_on_device, void* stream);
 /* per-band 1-D GP (sklearn GaussianProcessRegressor in the reference: ConstantKernel * RBF + WhiteKernel, four

@@ -57,6 +57,8 @@ def lib() -> C.CDLL:
     for name in ("mlrn_bazin", "mlrn_powerlaw", "mlrn_gp2d", "mlrn_gp1d"):
         if hasattr(L, name):
             getattr(L, name).argtypes = [vp, vp, vp, C.c_int, vp]
+    if hasattr(L, "mlrn_fits"):
+        L.mlrn_fits.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp]
     _lib = L
     return L
 

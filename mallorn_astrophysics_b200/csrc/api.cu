@@ -255,6 +255,54 @@ int mlrn_powerlaw(const mlrn_store* s, double* out, int32_t* status, int out_on_
   return with_status(s, out, status, out_on_device, MLRN_POWERLAW_COLS, 54, st,
                      [&](double* d, int32_t* ds) { return mlrn::run_powerlaw(s, d, ds, st); });
 }
+int mlrn_fits(const mlrn_store* s, double* bazin_out, int32_t* bazin_status, double* powerlaw_out,
+              int32_t* powerlaw_status, int out_on_device, void* stream) {
+  if (!s || !bazin_out || !powerlaw_out) { set_error("null store or output"); return MLRN_EINVAL; }
+  DevGuard g(s->device);
+  cudaStream_t st = (cudaStream_t)stream, side = nullptr;
+  if (!out_on_device) {                              // host buffers: device staging for all four tables, then the same call
+    const size_t n = (size_t)s->n_obj;
+    if (n == 0) return MLRN_OK;
+    const size_t nb = sizeof(double) * n * MLRN_BAZIN_COLS, np = sizeof(double) * n * MLRN_POWERLAW_COLS;
+    const size_t sb = bazin_status ? sizeof(int32_t) * n * 12 : 0, sp = powerlaw_status ? sizeof(int32_t) * n * 54 : 0;
+    unsigned char* d = nullptr;
+    const size_t off_p = nb, off_sb = nb + np, off_sp = nb + np + sb;       // doubles first: every table stays aligned
+    MLRN_CUDA(cudaMallocAsync(&d, nb + np + sb + sp, st));
+    int rc = mlrn_fits(s, (double*)d, sb ? (int32_t*)(d + off_sb) : nullptr, (double*)(d + off_p),
+                       sp ? (int32_t*)(d + off_sp) : nullptr, 1, stream);
+    if (rc == MLRN_OK) {
+      cudaError_t e = cudaMemcpyAsync(bazin_out, d, nb, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(powerlaw_out, d + off_p, np, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess && sb) e = cudaMemcpyAsync(bazin_status, d + off_sb, sb, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess && sp) e = cudaMemcpyAsync(powerlaw_status, d + off_sp, sp, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) rc = mlrn::cuda_fail(e, "mlrn_fits: copy of the rows to host");
+    }
+    cudaFreeAsync(d, st);
+    return rc;
+  }
+  cudaEvent_t fork = nullptr, join = nullptr;
+  cudaError_t e = cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&join, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventRecord(fork, st);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(side, fork, 0);
+  int rc = e == cudaSuccess ? MLRN_OK : mlrn::cuda_fail(e, "mlrn_fits: side stream");
+  if (rc == MLRN_OK) {
+    // Bazin first: its first stage is the longest kernel of the two passes and takes the SMs; the decline models fill
+    // them as its stage-0 CTAs retire and its few stragglers go on alone
+    rc = mlrn::run_bazin(s, bazin_out, bazin_status, st);
+    const int rc2 = mlrn::run_powerlaw(s, powerlaw_out, powerlaw_status, side);
+    if (rc == MLRN_OK) rc = rc2;
+    e = cudaEventRecord(join, side);                 // joined even after an error: nothing of the side stream may outlive the call's ordering
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, join, 0);
+    if (e != cudaSuccess && rc == MLRN_OK) rc = mlrn::cuda_fail(e, "mlrn_fits: join");
+  }
+  if (fork) cudaEventDestroy(fork);
+  if (join) cudaEventDestroy(join);
+  if (side) cudaStreamDestroy(side);                 // released by the runtime once its work has completed
+  return rc;
+}
 int mlrn_gp2d(const mlrn_store* s, double* out, int32_t* status, int out_on_device, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   return with_status(s, out, status, out_on_device, MLRN_GP2D_COLS, 4, st,

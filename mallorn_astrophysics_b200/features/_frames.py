@@ -34,7 +34,14 @@ def frames_from_store(store, ids, object_ids: Sequence, modules: Sequence[str], 
             zmap = pd.Series(metadata["Z"].to_numpy(dtype=np.float64), index=metadata["object_id"].to_numpy())
             zmap = zmap[~zmap.index.duplicated(keep="last")]
             z = zmap.reindex(ids).to_numpy(dtype=np.float64)
-        rows = {m: store.features(m, z=z if m in ("physics", "research") else None) for m in modules}
+        rows = {}
+        if "bazin" in modules and "powerlaw" in modules and hasattr(store, "fit_passes"):     # both fit passes in one overlapped call (mlrn_fits)
+            rows["bazin"] = np.empty((store.n_obj, len(schema.MODULE_COLUMNS["bazin"])), dtype=np.float64)
+            rows["powerlaw"] = np.empty((store.n_obj, len(schema.MODULE_COLUMNS["powerlaw"])), dtype=np.float64)
+            store.fit_passes(rows["bazin"], rows["powerlaw"])
+        for m in modules:
+            if m not in rows:
+                rows[m] = store.features(m, z=z if m in ("physics", "research") else None)
         counts = store.segments()[:, 0:21:3].sum(axis=1)
     finally:
         store.close()

@@ -86,16 +86,30 @@ def featurise_shard(cols: dict, n_local: int, modules: Sequence[str], table=None
     if on_pass:
         on_pass("pack")
     try:
-        c0 = 0
+        offs, c0 = {}, 0
+        for m in modules:
+            offs[m] = c0
+            c0 += _native.COLS[m]
+        pair = "bazin" in offs and "powerlaw" in offs          # both fit passes: one call, their straggler stages overlap (mlrn_fits)
         for m in modules:
             w = _native.COLS[m]
+            if pair and m in ("bazin", "powerlaw"):
+                if m != next(x for x in modules if x in ("bazin", "powerlaw")):
+                    continue                                   # done with the first of the two
+                rb = torch.empty((n_local, _native.COLS["bazin"]), dtype=torch.float64, device=f"cuda:{dev}")
+                rp = torch.empty((n_local, _native.COLS["powerlaw"]), dtype=torch.float64, device=f"cuda:{dev}")
+                store.fit_passes(rb, rp, status_bazin=(status or {}).get("bazin"), status_powerlaw=(status or {}).get("powerlaw"))
+                table[:, offs["bazin"]:offs["bazin"] + rb.shape[1]].copy_(rb)
+                table[:, offs["powerlaw"]:offs["powerlaw"] + rp.shape[1]].copy_(rp)
+                if on_pass:
+                    on_pass("bazin+powerlaw")
+                continue
             rows = torch.empty((n_local, w), dtype=torch.float64, device=f"cuda:{dev}")     # dense rows of this pass; freed (stream-ordered) after the copy
             z = cols.get("z") if m in ("physics", "research") else None
             if z is not None and not (hasattr(z, "is_cuda") and z.is_cuda):
                 z = torch.from_numpy(np.array(z, dtype=np.float64)).to(f"cuda:{dev}")
             store.features(m, z=z, out=rows, status=(status or {}).get(m))
-            table[:, c0:c0 + w].copy_(rows)
-            c0 += w
+            table[:, offs[m]:offs[m] + w].copy_(rows)
             if on_pass:
                 on_pass(m)
     finally:

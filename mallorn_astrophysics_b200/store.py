@@ -189,6 +189,31 @@ class LightCurveStore:
         _native.check(rc, f"mlrn pass '{module}'")
         return ret if ret is not None else out
 
+    def fit_passes(self, out_bazin, out_powerlaw, status_bazin=None, status_powerlaw=None, stream: Optional[int] = None):
+        """Bazin and decline-model passes in one call (``mlrn_fits``): the decline models run on an internal side stream
+        so that the straggler stages of the two passes overlap.  Outputs as in :meth:`features` (both on the same side);
+        results are those of the two separate passes."""
+        L = _native.lib()
+        st = self.stream if stream is None else int(stream)
+        bptr, bdev = _out_ptr(out_bazin, np.float64, (self.n_obj, _native.COLS["bazin"]), self.device, "out_bazin")
+        pptr, pdev = _out_ptr(out_powerlaw, np.float64, (self.n_obj, _native.COLS["powerlaw"]), self.device, "out_powerlaw")
+        if bdev != pdev:
+            raise ValueError("out_bazin and out_powerlaw must live on the same side")
+        sp = []
+        for status, scols, name in ((status_bazin, 12, "status_bazin"), (status_powerlaw, 54, "status_powerlaw")):
+            if status is None:
+                sp.append(0)
+                continue
+            n_stat = int(status.numel() if _is_torch(status) else status.size)
+            if n_stat != self.n_obj * scols:
+                raise ValueError(f"{name} must hold {scols} int32 values per object ({self.n_obj * scols}), got {n_stat}")
+            ptr, sdev = _out_ptr(status, np.int32, tuple(status.shape), self.device, name)
+            if sdev != bdev:
+                raise ValueError(f"{name} and the outputs must live on the same side")
+            sp.append(ptr)
+        _native.check(L.mlrn_fits(self._h, bptr, sp[0], pptr, sp[1], 1 if bdev else 0, st), "mlrn_fits")
+        return out_bazin, out_powerlaw
+
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h:
             _native.lib().mlrn_store_destroy(self._h)

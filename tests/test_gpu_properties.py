@@ -62,3 +62,26 @@ def test_reinterleaving_the_input_rows_changes_nothing(table):
     assert np.array_equal(seg, seg2)
     for m in MODULES:
         assert _same(shuffled[m], full[m]), m
+
+
+def test_the_overlapped_fit_call_equals_the_two_passes(table):
+    """mlrn_fits (Bazin on the caller's stream, decline models on an internal side stream) returns the rows and status
+    tables of mlrn_bazin + mlrn_powerlaw bit for bit, with host buffers and with device buffers."""
+    import torch
+    from mallorn_astrophysics_b200.store import LightCurveStore
+    sub = table.subset(6000)
+    with LightCurveStore.from_table(sub) as s:
+        sb, sp = np.zeros((s.n_obj, 6, 2), np.int32), np.zeros((s.n_obj, 27, 2), np.int32)
+        want_b, want_p = s.features("bazin", status=sb), s.features("powerlaw", status=sp)
+        hb, hp = np.empty_like(want_b), np.empty_like(want_p)
+        hsb, hsp = np.zeros_like(sb), np.zeros_like(sp)
+        s.fit_passes(hb, hp, status_bazin=hsb, status_powerlaw=hsp)
+        db = torch.empty(want_b.shape, dtype=torch.float64, device="cuda")
+        dp = torch.empty(want_p.shape, dtype=torch.float64, device="cuda")
+        dsb = torch.zeros(sb.shape, dtype=torch.int32, device="cuda")
+        s.fit_passes(db, dp, status_bazin=dsb)
+        torch.cuda.synchronize()
+    assert _same(hb, want_b) and _same(hp, want_p)
+    assert np.array_equal(hsb, sb) and np.array_equal(hsp, sp)
+    assert _same(db.cpu().numpy(), want_b) and _same(dp.cpu().numpy(), want_p)
+    assert np.array_equal(dsb.cpu().numpy(), sb)
