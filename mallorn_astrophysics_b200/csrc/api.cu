@@ -1,6 +1,7 @@
 // api.cu -- the C-ABI of libmallorn_b200.so (include/mallorn_b200.h).  Thin: argument checks,
 // host<->device staging, stream plumbing.  All arithmetic lives in the kernels.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX v3: ranges per C-ABI entry (tracing), visible in nsys / ncu timelines
 #include <atomic>
 #include <string>
 #include <new>
@@ -34,6 +35,7 @@ int run_research(const mlrn_store* s, const double* z_dev, double* out_dev, cuda
 using mlrn::set_error;
 
 namespace {
+struct NvtxRange { explicit NvtxRange(const char* name) { nvtxRangePushA(name); } ~NvtxRange() { nvtxRangePop(); } };
 
 struct DevGuard {
   int prev = -1;
@@ -99,6 +101,7 @@ int mlrn_device_count(void) {
 int mlrn_store_create(int device, int64_t n_rows, int32_t n_obj, const int32_t* obj, const uint8_t* band,
                       const double* t, const double* flux, const double* err, int inputs_on_device,
                       void* stream, mlrn_store** out) {
+  NvtxRange nvtx_("mlrn_store_create");
   if (!out) { set_error("out is null"); return MLRN_EINVAL; }
   *out = nullptr;
   if (n_rows < 0 || n_obj < 0 || (n_rows > 0 && (!obj || !band || !t || !flux || !err))) {
@@ -195,23 +198,28 @@ int mlrn_store_export(const mlrn_store* s, int64_t* seg_off, double* t, double* 
 }
 
 int mlrn_stat(const mlrn_store* s, double* out, int out_on_device, void* stream) {
+  NvtxRange nvtx_("mlrn_stat");
   cudaStream_t st = (cudaStream_t)stream;
   return with_output(s, out, out_on_device, MLRN_STAT_COLS, st, [&](double* d) { return mlrn::run_stat(s, d, st); });
 }
 
 int mlrn_color(const mlrn_store* s, double* out, int out_on_device, void* stream) {
+  NvtxRange nvtx_("mlrn_color");
   cudaStream_t st = (cudaStream_t)stream;
   return with_output(s, out, out_on_device, MLRN_COLOR_COLS, st, [&](double* d) { return mlrn::run_color(s, d, st); });
 }
 int mlrn_shape(const mlrn_store* s, double* out, int out_on_device, void* stream) {
+  NvtxRange nvtx_("mlrn_shape");
   cudaStream_t st = (cudaStream_t)stream;
   return with_output(s, out, out_on_device, MLRN_SHAPE_COLS, st, [&](double* d) { return mlrn::run_shape(s, d, st); });
 }
 int mlrn_tde(const mlrn_store* s, double* out, int out_on_device, void* stream) {
+  NvtxRange nvtx_("mlrn_tde");
   cudaStream_t st = (cudaStream_t)stream;
   return with_output(s, out, out_on_device, MLRN_TDE_COLS, st, [&](double* d) { return mlrn::run_tde(s, d, st); });
 }
 int mlrn_physics(const mlrn_store* s, const double* z, int z_on_device, double* out, int out_on_device, void* stream) {
+  NvtxRange nvtx_("mlrn_physics");
   if (!s || !z) { set_error("null store or redshift column"); return MLRN_EINVAL; }
   cudaStream_t st = (cudaStream_t)stream;
   DevGuard g(s->device);
@@ -229,6 +237,7 @@ int mlrn_physics(const mlrn_store* s, const double* z, int z_on_device, double* 
 }
 
 int mlrn_research(const mlrn_store* s, const double* z, int z_on_device, double* out, int out_on_device, void* stream) {
+  NvtxRange nvtx_("mlrn_research");
   if (!s) { set_error("null store"); return MLRN_EINVAL; }
   cudaStream_t st = (cudaStream_t)stream;
   DevGuard g(s->device);
@@ -246,17 +255,20 @@ int mlrn_research(const mlrn_store* s, const double* z, int z_on_device, double*
 }
 
 int mlrn_bazin(const mlrn_store* s, double* out, int32_t* status, int out_on_device, void* stream) {
+  NvtxRange nvtx_("mlrn_bazin");
   cudaStream_t st = (cudaStream_t)stream;
   return with_status(s, out, status, out_on_device, MLRN_BAZIN_COLS, 12, st,
                      [&](double* d, int32_t* ds) { return mlrn::run_bazin(s, d, ds, st); });
 }
 int mlrn_powerlaw(const mlrn_store* s, double* out, int32_t* status, int out_on_device, void* stream) {
+  NvtxRange nvtx_("mlrn_powerlaw");
   cudaStream_t st = (cudaStream_t)stream;
   return with_status(s, out, status, out_on_device, MLRN_POWERLAW_COLS, 54, st,
                      [&](double* d, int32_t* ds) { return mlrn::run_powerlaw(s, d, ds, st); });
 }
 int mlrn_fits(const mlrn_store* s, double* bazin_out, int32_t* bazin_status, double* powerlaw_out,
               int32_t* powerlaw_status, int out_on_device, void* stream) {
+  NvtxRange nvtx_("mlrn_fits");
   if (!s || !bazin_out || !powerlaw_out) { set_error("null store or output"); return MLRN_EINVAL; }
   DevGuard g(s->device);
   cudaStream_t st = (cudaStream_t)stream, side = nullptr;
@@ -304,11 +316,13 @@ int mlrn_fits(const mlrn_store* s, double* bazin_out, int32_t* bazin_status, dou
   return rc;
 }
 int mlrn_gp2d(const mlrn_store* s, double* out, int32_t* status, int out_on_device, void* stream) {
+  NvtxRange nvtx_("mlrn_gp2d");
   cudaStream_t st = (cudaStream_t)stream;
   return with_status(s, out, status, out_on_device, MLRN_GP2D_COLS, 4, st,
                      [&](double* d, int32_t* ds) { return mlrn::run_gp2d(s, d, ds, st); });
 }
 int mlrn_gp1d(const mlrn_store* s, double* out, int32_t* status, int out_on_device, void* stream) {
+  NvtxRange nvtx_("mlrn_gp1d");
   cudaStream_t st = (cudaStream_t)stream;
   return with_status(s, out, status, out_on_device, MLRN_GP1D_COLS, 12, st,
                      [&](double* d, int32_t* ds) { return mlrn::run_gp1d(s, d, ds, st); });

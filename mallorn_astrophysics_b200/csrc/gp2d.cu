@@ -774,7 +774,10 @@ int run_gp2d(const mlrn_store* s, double* out_dev, int* status_dev, cudaStream_t
   MLRN_CUDA(cudaMemsetAsync(s->ticket + 2, 0, 2 * sizeof(unsigned long long), st));
   k_gp2d<true><<<grid1, GP_THREADS, smem1, st>>>(s->seg_off, s->t, s->flux, s->err, s->rank, s->n_obj, T1, 0, T1 * TB,
                                                  nullptr, cache, s->ticket + 2, out_dev, status_dev);
-  MLRN_CUDA(cudaGetLastError());
+  {
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { cudaFreeAsync(cache, st); return cuda_fail(e, "k_gp2d launch"); }
+  }
   count_launch();
   if (any_beyond) {
     double* scratch = nullptr;
