@@ -49,6 +49,7 @@ constexpr int COOP_FITS_PER_WARP = 4;          // a resumed stage with at most t
 template <class Job> struct FitCarry { Job job; long long fit; };
 
 struct StageIo {
+  const double* pre;                // stage 0: [ticket][Job::PRE] start values from the prologue pass; nullptr: computed in place
   const unsigned* order;            // stage 0: ticket -> fit (sorted by row count, longest first); nullptr: ticket = fit
   unsigned long long* ticket;        // this stage's work counter
   int cap;                           // function evaluations after which a running fit moves on (INT_MAX: never)
@@ -67,12 +68,18 @@ struct BazinPolicyT {
     const int b = (int)(fit / n_obj); const long long o = fit % n_obj;
     return (int)(seg_off[o * N_SEG + b + 1] - seg_off[o * N_SEG + b]);
   }
-  __device__ bool start(Job& job, long long fit) const {
+  __device__ void prologue(Job& job, long long fit, double* pre_out) const {      // the start values of the fit, nothing else
+    const int b = (int)(fit / n_obj); const long long o = fit % n_obj;
+    const long long lo = seg_off[o * N_SEG + b];
+    int code;
+    job.init(gt + lo, gf + lo, ge + lo, (int)(seg_off[o * N_SEG + b + 1] - lo), code, nullptr, pre_out);
+  }
+  __device__ bool start(Job& job, long long fit, const double* pre) const {
     const int b = (int)(fit / n_obj); const long long o = fit % n_obj;
     const long long lo = seg_off[o * N_SEG + b];
     const int n = (int)(seg_off[o * N_SEG + b + 1] - lo);
     int code;
-    if (job.init(gt + lo, gf + lo, ge + lo, n, code)) return true;
+    if (job.init(gt + lo, gf + lo, ge + lo, n, code, pre)) return true;
     job.finish(code, out + o * BAZIN_COLS + 8 * b);
     if (status) { status[(o * N_BAND + b) * 2] = code; status[(o * N_BAND + b) * 2 + 1] = 0; }
     return false;
@@ -105,14 +112,22 @@ struct DeclinePolicyT {
     const int j = rem / PER_BAND, q = (KIND == 0) ? rem % PER_BAND : (KIND == 1 ? 7 : 8);
     return o * POWERLAW_COLS + 9 * j + q;
   }
-  __device__ bool start(Job& job, long long fit) const {
+  __device__ void prologue(Job& job, long long fit, double* pre_out) const {
+    const int rem = (int)(fit / n_obj); const long long o = fit % n_obj;
+    const int j = rem / PER_BAND, q = rem % PER_BAND;
+    const int band = (j == 0) ? BG : (j == 1 ? BR : BI);
+    const long long lo = seg_off[o * N_SEG + band];
+    int code;
+    job.init(gt + lo, gf + lo, (int)(seg_off[o * N_SEG + band + 1] - lo), (KIND == 0) ? decline_index(q) : 0.0, code, nullptr, pre_out);
+  }
+  __device__ bool start(Job& job, long long fit, const double* pre) const {
     const int rem = (int)(fit / n_obj); const long long o = fit % n_obj;
     const int j = rem / PER_BAND, q = rem % PER_BAND;
     const int band = (j == 0) ? BG : (j == 1 ? BR : BI);
     const long long lo = seg_off[o * N_SEG + band];
     const int n = (int)(seg_off[o * N_SEG + band + 1] - lo);
     int code;
-    if (job.init(gt + lo, gf + lo, n, (KIND == 0) ? decline_index(q) : 0.0, code)) return true;
+    if (job.init(gt + lo, gf + lo, n, (KIND == 0) ? decline_index(q) : 0.0, code, pre)) return true;
     const long long s = slot(fit);
     out[s] = qnan();
     if (status) { status[s * 2] = code; status[s * 2 + 1] = 0; }
@@ -168,6 +183,21 @@ __global__ void __launch_bounds__(256) k_fit_scatter(P pol, unsigned* __restrict
 
 // COOP = false: one thread per fit.  COOP = true: one WARP per fit (resumed stages only); `coop_limit`: the largest survivor
 // count the cooperative launch takes -- the two launches of a resumed stage read the same count and exactly one of them works.
+// PROLOGUE.  A fit starts with two passes over its band that only the lane holding it can run while the other 31 wait in
+// the middle of their own fits -- the median of the fluxes (rank counting, O(n^2)) and the cost at the start (n model
+// evaluations): 5 % of the warp instructions of the stage-0 kernel at ONE thread per instruction.  Here they are computed
+// for every fit up front, one thread per ticket (a warp's lanes have the same row count in the work order), and stage 0
+// reads Job::PRE doubles per ticket instead.  Same functions on the same data: the values are bit-identical.  Bazin at 10^6
+// objects 2.33 -> 2.26 s; not used for the decline models (Job::PRE = 0: their start costs one short pass).
+template <class P>
+__global__ void __launch_bounds__(128) k_fit_prologue(P pol, const unsigned* __restrict__ order, double* __restrict__ pre) {
+  const long long total = pol.total();
+  for (long long tk = blockIdx.x * (long long)blockDim.x + threadIdx.x; tk < total; tk += (long long)gridDim.x * blockDim.x) {
+    typename P::Job job;
+    pol.prologue(job, order ? (long long)order[tk] : tk, pre + tk * P::Job::PRE);
+  }
+}
+
 #ifdef FIT_STATS
 __device__ unsigned long long g_fit_stats[8];   // warp trips, active lanes, lanes with a Jacobian pass, rows (sum, max), rows of the passes (sum, max), trips with a pass
 #endif
@@ -200,7 +230,7 @@ __global__ void __launch_bounds__(FIT_THREADS, FIT_MIN_BLOCKS) k_fit_stage(P pol
       if (COOP) tk = __shfl_sync(0xffffffffu, tk, 0);               // one ticket per warp
       if (tk >= total) { exhausted = true; break; }
       if (in) { job = in[tk].job; fit = in[tk].fit; active = true; }
-      else { fit = io.order ? (long long)io.order[tk] : tk; active = pol.start(job, fit); }
+      else { fit = io.order ? (long long)io.order[tk] : tk; active = pol.start(job, fit, (Job::PRE > 0 && io.pre) ? io.pre + tk * Job::PRE : nullptr); }
     }
     if (!__syncthreads_or(active || !exhausted)) break;      // also lines the warps up: they fetch the same code
 #ifdef FIT_STATS
@@ -288,6 +318,17 @@ int run_staged(const mlrn_store* s, const P& pol, long long fits, const int* cap
       e = cudaGetLastError();
     }
   }
+  double* pre = nullptr;                              // [fits][Job::PRE] start values of every fit (prologue pass)
+  if (e == cudaSuccess && P::Job::PRE > 0 && fits > 64 && !getenv("MLRN_FIT_NO_PROLOGUE")) {
+    e = cudaMallocAsync(&pre, sizeof(double) * (size_t)fits * P::Job::PRE, st);
+    if (e == cudaSuccess) {
+      long long blocks = (fits + 127) / 128;
+      if (blocks > (long long)s->sm_count * 16) blocks = (long long)s->sm_count * 16;
+      k_fit_prologue<P><<<(int)blocks, 128, 0, st>>>(pol, order, pre);
+      count_launch();
+      e = cudaGetLastError();
+    }
+  }
   if (e == cudaSuccess && n_caps > 0) e = cudaMallocAsync(&buf[0], sizeof(Carry) * (size_t)capacity, st);
   if (e == cudaSuccess && n_caps > 1) e = cudaMallocAsync(&buf[1], sizeof(Carry) * (size_t)capacity, st);
   if (e == cudaSuccess) {
@@ -295,6 +336,7 @@ int run_staged(const mlrn_store* s, const P& pol, long long fits, const int* cap
     for (int stage = 0; stage <= n_caps; ++stage) {
       StageIo io;
       io.order = stage == 0 ? order : nullptr;
+      io.pre = stage == 0 ? pre : nullptr;
       io.ticket = ctr + stage;
       io.cap = stage < n_caps ? caps[stage] : INT_MAX;
       io.in = stage > 0 ? buf[(stage - 1) & 1] : nullptr;
@@ -320,6 +362,7 @@ int run_staged(const mlrn_store* s, const P& pol, long long fits, const int* cap
   if (buf[0]) cudaFreeAsync(buf[0], st);
   if (buf[1]) cudaFreeAsync(buf[1], st);
   if (order) cudaFreeAsync(order, st);
+  if (pre) cudaFreeAsync(pre, st);
   cudaFreeAsync(ctr, st);
   if (e != cudaSuccess) return cuda_fail(e, "staged fit launch");
   return MLRN_OK;

@@ -142,14 +142,19 @@ struct TrfThread {
   }
 
   // Returns TRF_RUNNING or a final status / TrfFail code.
-  MLRN_FN int begin(const Model& model, int rows, const double* x0, const double* lo, const double* hi, int maxfev) {
+  // cost_in: the cost at the (strictly feasible) start computed earlier by the prologue pass of fits.cu -- NaN stands for
+  // a non-finite residual -- instead of a pass over the rows here; cost_out: where that pass leaves it
+  MLRN_FN int begin(const Model& model, int rows, const double* x0, const double* lo, const double* hi, int maxfev,
+                    const double* cost_in = nullptr, double* cost_out = nullptr) {
     mdl = model; m = rows; max_nfev = maxfev; nfev = 0; status = -1; cost = qnan();
     for (int i = 0; i < NP; ++i) { x[i] = x0[i]; lb[i] = lo[i]; ub[i] = hi[i]; }
     for (int i = 0; i < NP; ++i) if (!(lb[i] < ub[i])) return TRF_BAD_BOUNDS;
     if (!in_bounds<NP>(x, lb, ub)) return TRF_X0_INFEASIBLE;
     make_strictly_feasible<NP>(x, lb, ub, 1e-10);
     bool finite;
-    cost = residual_cost(x, finite);
+    if (cost_in) { cost = *cost_in; finite = !is_nan(cost); }
+    else cost = residual_cost(x, finite);
+    if (cost_out) *cost_out = finite ? cost : qnan();
     nfev = 1;
     if (!finite) return TRF_F0_NONFINITE;
     need_jac = true; alpha = 0.0; Delta = -1.0;     // Delta < 0: initialise after the first gradient
