@@ -324,7 +324,7 @@ __device__ __forceinline__ void gp_eval(const GpShared& S, double* __restrict__ 
   double* cache_s = cache;
   double* cache_e = cache + (size_t)n_tiles(T_cap) * TT;
   // ---- (a) kernel matrix, b = y - mean
-  // e = storage index: tile, then fragment order.  Branch-free body, two elements per trip: the sqrt and exp chains of
+  // e = storage index: tile, then fragment order.  Several elements per trip: the sqrt and exp chains of
   // the pair interleave (the loop is bound by FP64 latency, not by its 4 shared-memory loads).
   auto element = [&](int e) {
     const int tl = e >> 8;
@@ -332,14 +332,15 @@ __device__ __forceinline__ void gp_eval(const GpShared& S, double* __restrict__ 
     tix_decode(e & 255, r, c);
     const int gi = S.tI[tl] * TB + r, gj = S.tJ[tl] * TB + c;
     const bool ok = gi < n && gj < n;
-    const int ia = ok ? gi : 0, ib = ok ? gj : 0;
-    const double dt = S.st[ia] - S.st[ib], dl = S.sl[ia] - S.sl[ib];
+    if (!ok) { S.tiles[e] = (gi == gj) ? 1.0 : 0.0; return; }      // padding of the last tile row / column (12 % of the elements at N = 150): no kernel value to compute (+2 %)
+    // (measured and rejected: computing only the lower half of the diagonal tiles and mirroring it: 125.4 k against 130.5 k objects/s)
+    const double dt = S.st[gi] - S.st[gj], dl = S.sl[gi] - S.sl[gj];
     const double s = sqrt(3.0 * (dt * dt * kp.im0 + dl * dl * kp.im1));
     const double ex = exp(-s);
     double v = kp.amp * (1.0 + s) * ex;
-    if (gi == gj) v += S.sn[ia];
-    if (ok) { cache_s[e] = s; cache_e[e] = ex; }
-    S.tiles[e] = ok ? v : ((gi == gj) ? 1.0 : 0.0);
+    if (gi == gj) v += S.sn[gi];
+    cache_s[e] = s; cache_e[e] = ex;
+    S.tiles[e] = v;
   };
   {
     int e = tid;
