@@ -226,6 +226,7 @@ __device__ __forceinline__ void tile_update(double* __restrict__ C, const double
   for (int ri = 0; ri < 2; ++ri)
 #pragma unroll
     for (int ci = 0; ci < 2; ++ci) { const double2 v = C2[(ri * 2 + ci) * 32 + lane]; acc[ri][ci][0] = v.x; acc[ri][ci][1] = v.y; }
+  // (measured and rejected: loading the fragments once when Vi == Vj, the diagonal tiles: 128.5 k against 130.7 k objects/s)
   dmma_16x16x16(acc, Vi, VLD, Vj, VLD, true);
 #pragma unroll
   for (int ri = 0; ri < 2; ++ri)
@@ -379,6 +380,10 @@ __device__ __forceinline__ void gp_eval(const GpShared& S, double* __restrict__ 
     // Also measured in round 2 and rejected: letting those warps start on bulk tasks at once -- the pivot chain slows
     // from 4.5 k to 5.1 k cycles, 118.6 k objects/s against 121.7 k; and scaling the next step's V inside this phase behind
     // flags instead of the scale barrier -- the scales then wait for the pivot chain, 104.9 k objects/s.)
+    // (Round 2, final build, measured and rejected: the spare warps taking TWO tasks each from the start whenever that saves
+    // the bulk warps a round (54 tasks = 4 x 12 + 6 at T = 10): the pivot slows from 4.2 k to 5.0 k cycles and the bulk tasks
+    // from 1.18 k to 1.37 k each -- the phase is bound by shared-memory bandwidth, not by who issues it; 126.5 k against
+    // 130.6 k objects/s.)
     const int n_help = (has_next && (ntask % N_BULK) >= 1 && (ntask % N_BULK) <= GP_WARPS / 4 - 1) ? (ntask % N_BULK) : 0;
     // ---- phase A: V_i = X_i Li^T for i != k, one warp per tile row.  The pivot warp takes row k+1 and then runs AHEAD
     // of the barrier (it only arrives): the update of tile (k+1, k+1), of b_{k+1} and the factorisation need V_{k+1} only.
@@ -660,8 +665,14 @@ k_gp2d(const long long* __restrict__ seg_off, const double* __restrict__ gt, con
       const double xk[4] = {s_opt.x[0], s_opt.x[1], s_opt.x[2], s_opt.x[3]};
       gp_eval(S, cache, n, T, T_cap, xk, f, g);        // ends with a barrier: everyone has read x
       if (!searching) { f_fin = f; break; }            // that was the evaluation at the optimum (alpha for predict)
+#ifdef GP_PHASE_TIMING
+      const long long adv_t0 = clock64();
+#endif
       if (tid == 0) s_go = s_opt.advance(f, g) ? 1 : 0;
       __syncthreads();
+#ifdef GP_PHASE_TIMING
+      if (blockIdx.x == 0 && tid == 0) atomicAdd(&g_gp_phase[7], (unsigned long long)(clock64() - adv_t0));      // optimiser step (thread 0) + barrier
+#endif
       if (!s_go) {
         // The search normally ends at the point it evaluated last (a successful line search): alpha of the optimum is
         // still in S.sb and the evaluation the reference repeats for predict() would reproduce it bit for bit -- skipped

@@ -21,7 +21,7 @@ with LightCurveStore.from_table(table) as s:
     s.features("gp2d", status=st)
     L.mlrn_gp_phase_cycles(buf, 0)
     if has_w: L.mlrn_gp_warp_cycles(wbuf, 0)
-names = ["build", "pivot0", "phaseA(scale)+sync", "warp0: tile update + b", "phaseB tail wait (sync)", "gradient", "warp0: pivot", "-"]
+names = ["build", "pivot0", "phaseA(scale)+sync", "warp0: tile update + b", "phaseB tail wait (sync)", "gradient", "warp0: pivot", "optimiser step (thread 0) + barrier"]
 tot = sum(buf[:8])
 for k, nm in enumerate(names):
     if buf[k]: print(f"{nm:28s} {buf[k]:14d} cycles  {100*buf[k]/tot:5.1f}%")
