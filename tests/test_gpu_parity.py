@@ -281,3 +281,26 @@ def test_statistical_fast_path_corner_cases():
         warnings.simplefilter("ignore")
         present, want = run_table("statistical", table)
     _compare(got[present], want, rtol=1e-5, atol=1e-9, what="statistical/corner cases")
+
+
+def test_non_finite_fluxes_stay_with_their_object():
+    """An object with NaN / inf fluxes takes the general moment kernel (the fast path declines it) and every pass still
+    returns: the rows of all OTHER objects are bit for bit those of the same batch with that object's fluxes finite."""
+    from mallorn_astrophysics_b200.store import LightCurveStore
+    from mallorn_astrophysics_b200.synth import make_table
+    tb = make_table(64, seed=5)
+    bad = tb.flux.copy()
+    rows = np.flatnonzero(tb.obj == 17)
+    bad[rows[3]] = np.nan
+    bad[rows[7]] = np.inf
+    bad[rows[11]] = -np.inf
+    out = {}
+    for name, flux in (("clean", tb.flux), ("bad", bad)):
+        with LightCurveStore(tb.obj, tb.band, tb.t, flux, tb.err, tb.n_obj) as s:
+            out[name] = {m: s.features(m, z=tb.z if m == "physics" else None)
+                         for m in ("statistical", "colors", "shape", "tde", "physics", "bazin", "powerlaw", "gp2d")}
+    others = np.arange(tb.n_obj) != 17
+    for m, a in out["clean"].items():
+        b = out["bad"][m]
+        assert np.array_equal(a[others].view(np.uint64), b[others].view(np.uint64)), m
+    assert out["bad"]["statistical"][17, 0] >= 0          # n_obs of the first band is still a count
