@@ -63,12 +63,13 @@ MLRN_FN void stage_object(const Team& tm, const long long* seg_off, const double
 template <class Team>
 MLRN_FN int argmax_file_order(const Team& tm, const ObjView& v, int lo, int hi) {
   // two reductions: the max value, then the smallest rank among the elements attaining it
-  double m = -pinf();
-  for (int i = lo + tm.rank(); i < hi; i += Team::size) m = fmax(m, v.f[i]);
+  double m = -pinf(); int any_nan = 0;
+  for (int i = lo + tm.rank(); i < hi; i += Team::size) { m = fmax(m, v.f[i]); any_nan |= is_nan(v.f[i]) ? 1 : 0; }
   m = tm.max(m);
+  any_nan = tm.imax(any_nan);                        // numpy.argmax: the first NaN is the maximum
   int best = 0x7fffffff;
   for (int i = lo + tm.rank(); i < hi; i += Team::size)
-    if (v.f[i] == m) { int key = ((int)v.rank[i] << 11) | (i - lo); if (key < best) best = key; }
+    if (any_nan ? is_nan(v.f[i]) : (v.f[i] == m)) { int key = ((int)v.rank[i] << 11) | (i - lo); if (key < best) best = key; }
   best = tm.imin(best);
   return (best == 0x7fffffff) ? -1 : lo + (best & 2047);
 }

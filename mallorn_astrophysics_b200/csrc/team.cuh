@@ -50,6 +50,10 @@ MLRN_FN_FORCE double pinf() {
 #endif
 }
 MLRN_FN_FORCE bool is_nan(double x) { return x != x; }
+// orderings in which a NaN is the extreme value, as numpy.argmax / argmin treat it (the first NaN wins)
+MLRN_FN_FORCE bool nan_gt(double a, double b) { return a > b || (a != a && b == b); }
+MLRN_FN_FORCE bool nan_lt(double a, double b) { return a < b || (a != a && b == b); }
+MLRN_FN_FORCE bool nan_eq(double a, double b) { return a == b || (a != a && b != b); }
 MLRN_FN_FORCE bool is_finite(double x) { return fabs(x) < pinf(); }
 #ifndef __CUDACC__
 inline double rsqrt(double x) { return 1.0 / sqrt(x); }   // host instantiation only (tests/hostsim)
@@ -90,24 +94,27 @@ struct WarpTeam {
   __device__ __forceinline__ double bcast(double v, int src) const { return __shfl_sync(FULL, v, src); }
   __device__ __forceinline__ int ibcast(int v, int src) const { return __shfl_sync(FULL, v, src); }
 
-  // index of the largest value; ties -> smallest index; idx < 0 marks "no candidate"
+  // index of the largest value; ties -> smallest index; idx < 0 marks "no candidate".  A NaN counts as larger than every
+  // number and equal to another NaN (numpy.argmax returns the first NaN): the relation is a total order, so every lane ends
+  // with the SAME index -- with plain comparisons a NaN made the lanes disagree, and the team-collective code that follows
+  // (compactions, sorts) ran with lane-dependent sizes.
   __device__ __forceinline__ int argmax_first(double v, int idx) const {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       double ov = __shfl_xor_sync(FULL, v, o);
       int oi = __shfl_xor_sync(FULL, idx, o);
-      bool take = (oi >= 0) && (idx < 0 || ov > v || (ov == v && oi < idx));
+      bool take = (oi >= 0) && (idx < 0 || nan_gt(ov, v) || (nan_eq(ov, v) && oi < idx));
       if (take) { v = ov; idx = oi; }
     }
     return idx;
   }
-  // index of the smallest value; ties -> smallest index
+  // index of the smallest value; ties -> smallest index (a NaN counts as smaller than every number: numpy.argmin)
   __device__ __forceinline__ int argmin_first(double v, int idx) const {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       double ov = __shfl_xor_sync(FULL, v, o);
       int oi = __shfl_xor_sync(FULL, idx, o);
-      bool take = (oi >= 0) && (idx < 0 || ov < v || (ov == v && oi < idx));
+      bool take = (oi >= 0) && (idx < 0 || nan_lt(ov, v) || (nan_eq(ov, v) && oi < idx));
       if (take) { v = ov; idx = oi; }
     }
     return idx;
@@ -230,7 +237,7 @@ MLRN_FN int team_argmax_first(const Team& tm, const double* a, int n) {
   double bv = 0.0; int bi = -1;
   for (int i = tm.rank(); i < n; i += Team::size) {
     double v = a[i];
-    if (bi < 0 || v > bv) { bv = v; bi = i; }
+    if (bi < 0 || nan_gt(v, bv)) { bv = v; bi = i; }
   }
   return tm.argmax_first(bv, bi);
 }
@@ -240,7 +247,7 @@ MLRN_FN int team_argmin_first(const Team& tm, const double* a, int n) {
   double bv = 0.0; int bi = -1;
   for (int i = tm.rank(); i < n; i += Team::size) {
     double v = a[i];
-    if (bi < 0 || v < bv) { bv = v; bi = i; }
+    if (bi < 0 || nan_lt(v, bv)) { bv = v; bi = i; }
   }
   return tm.argmin_first(bv, bi);
 }
