@@ -71,8 +71,8 @@ def featurise_shard(cols: dict, n_local: int, modules: Sequence[str], table=None
     """One rank's share of the work: pack the shard's flat columns (``obj`` already re-based to ``0..n_local``; host arrays or
     CUDA tensors) into one store and run every pass of ``modules`` on it, writing the rows side by side into ONE
     ``[n_local, table_width(modules)]`` float64 CUDA table (module order = column order).  Nothing is synchronised:
-    everything is ordered on ``stream``; ``on_pass(name)`` is called after each launch sequence (the bench records events
-    there).  ``cols['z']`` (per-object redshift) is used by the physics pass when present."""
+    everything is ordered on ``stream``; ``on_pass(name)`` is called after each launch sequence and, as ``on_pass('table')``,
+    after the copy of a pass's rows into the wide table (the bench records events there).  ``cols['z']`` (per-object redshift) is used by the physics pass when present."""
     import torch
     from . import _native
     from .store import LightCurveStore
@@ -99,19 +99,23 @@ def featurise_shard(cols: dict, n_local: int, modules: Sequence[str], table=None
                 rb = torch.empty((n_local, _native.COLS["bazin"]), dtype=torch.float64, device=f"cuda:{dev}")
                 rp = torch.empty((n_local, _native.COLS["powerlaw"]), dtype=torch.float64, device=f"cuda:{dev}")
                 store.fit_passes(rb, rp, status_bazin=(status or {}).get("bazin"), status_powerlaw=(status or {}).get("powerlaw"))
+                if on_pass:
+                    on_pass("bazin+powerlaw")
                 table[:, offs["bazin"]:offs["bazin"] + rb.shape[1]].copy_(rb)
                 table[:, offs["powerlaw"]:offs["powerlaw"] + rp.shape[1]].copy_(rp)
                 if on_pass:
-                    on_pass("bazin+powerlaw")
+                    on_pass("table")
                 continue
             rows = torch.empty((n_local, w), dtype=torch.float64, device=f"cuda:{dev}")     # dense rows of this pass; freed (stream-ordered) after the copy
             z = cols.get("z") if m in ("physics", "research") else None
             if z is not None and not (hasattr(z, "is_cuda") and z.is_cuda):
                 z = torch.from_numpy(np.array(z, dtype=np.float64)).to(f"cuda:{dev}")
             store.features(m, z=z, out=rows, status=(status or {}).get(m))
+            if on_pass:
+                on_pass(m)                                     # the pass's own launches ...
             table[:, offs[m]:offs[m] + w].copy_(rows)
             if on_pass:
-                on_pass(m)
+                on_pass("table")                               # ... and the copy of its rows into the wide table, marked separately
     finally:
         # destroying the store frees its arrays with cudaFree, which waits for the device: the passes above are complete
         store.close()
