@@ -1,0 +1,4 @@
+#!/bin/bash
+set -x
+timeout 900 python -m pytest tests/test_gpu_gp2d.py -m gpu -x -q 2>&1 | tail -3
+timeout 300 python tests/gpu_rate.py gp2d 100000 3
