@@ -43,7 +43,10 @@ namespace {
 #endif
 constexpr int FIT_THREADS = FIT_THREADS_N;     // warps of one CTA start every trip together (see the barrier in the loop)
 constexpr int MAX_STAGES = 6;
-constexpr int COOP_FITS_PER_WARP = 4;          // a resumed stage with at most this many survivors per warp runs them cooperatively
+#ifndef COOP_FITS_N
+#define COOP_FITS_N 4
+#endif
+constexpr int COOP_FITS_PER_WARP = COOP_FITS_N;          // a resumed stage with at most this many survivors per warp runs them cooperatively
 
 // a fit that outlived its stage: the whole resumable job and which fit it is
 template <class Job> struct FitCarry { Job job; long long fit; };
@@ -384,7 +387,15 @@ namespace {
 #define FIT_STAGE_CAPS {96, 192, 384, 768}
 #endif
 #ifndef FIT_DECLINE_CAPS
+#if defined(FIT_DECLINE_SET) && FIT_DECLINE_SET == 1      // developer sweeps (nvcc splits -D values at commas)
+#define FIT_DECLINE_CAPS {48, 192}
+#elif defined(FIT_DECLINE_SET) && FIT_DECLINE_SET == 2
+#define FIT_DECLINE_CAPS {96, 384}
+#elif defined(FIT_DECLINE_SET) && FIT_DECLINE_SET == 3
+#define FIT_DECLINE_CAPS {48, 96, 192, 384}
+#else
 #define FIT_DECLINE_CAPS {64, 256}
+#endif
 #endif
 
 }  // namespace
