@@ -178,4 +178,14 @@ int hs_gp1d(long long n_obj, const long long* seg_off, const double* t, const do
 }
 
 
+// the two division helpers of the fit models (trf.cuh, fits.cuh): out[i] = {div_r(a, d, 1 / d), a / d} and, for the
+// curve's own division, {div_curve(a, d), a / d}
+void hs_div_helpers(long long n, const double* a, const double* d, double* out_r, double* out_curve, double* out_ieee) {
+  for (long long i = 0; i < n; ++i) {
+    out_r[i] = div_r(a[i], d[i], 1.0 / d[i]);
+    out_curve[i] = div_curve(a[i], d[i]);
+    out_ieee[i] = a[i] / d[i];
+  }
+}
+
 }  // extern "C"

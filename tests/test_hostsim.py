@@ -189,3 +189,25 @@ def test_research_template_matches_reference(golden, hs, fixture):
     assert np.array_equal(np.isnan(got), np.isnan(ref))
     ok = ~np.isnan(ref)
     np.testing.assert_allclose(got[ok], ref[ok], rtol=1e-7, atol=1e-9)
+
+
+def test_division_helpers_of_the_fit_models_equal_ieee_division(hs):
+    """``div_r`` (a / d from a correctly rounded reciprocal: one multiplication and a residual correction) over the operand
+    ranges of a fit pass, and ``div_curve`` (exact shortcuts for a zero numerator / an infinite denominator) on exactly
+    those operands, against the IEEE quotient."""
+    rng = np.random.default_rng(12)
+    n = 2_000_000
+    d = np.ldexp(rng.uniform(0.5, 1.0, n), rng.integers(-20, 20, n))                    # time scales, finite-difference steps
+    a = np.ldexp(rng.uniform(0.5, 1.0, n), rng.integers(-30, 30, n)) * rng.choice([-1.0, 1.0], n)
+    a[:1000] = 0.0
+    with np.errstate(over="ignore", under="ignore"):
+        den = 1.0 + np.exp(rng.uniform(-800.0, 800.0, n))                               # [1, +inf]
+        num = np.exp(rng.uniform(-800.0, 700.0, n)) * rng.uniform(0.0, 1e4, n)          # [0, large], zeros by underflow
+    P = ctypes.POINTER(ctypes.c_double)
+    out = [np.empty(n) for _ in range(3)]
+    with np.errstate(all="ignore"):
+        hs.hs_div_helpers(ctypes.c_longlong(n), a.ctypes.data_as(P), d.ctypes.data_as(P), *[o.ctypes.data_as(P) for o in out])
+        assert np.array_equal(out[0].view(np.uint64), out[2].view(np.uint64))
+        hs.hs_div_helpers(ctypes.c_longlong(n), num.ctypes.data_as(P), den.ctypes.data_as(P), *[o.ctypes.data_as(P) for o in out])
+        assert np.isinf(den).any() and (num == 0.0).any()
+        assert np.array_equal(out[1].view(np.uint64), out[2].view(np.uint64))
