@@ -9,9 +9,13 @@ own entry points (``shard.featurise_shard`` / ``shard.featurise_sharded``).
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c4|c5|c1|c2|c3]
 
 * N = 1 (default ``--config c4``): BASELINE.json configs[3], 10^6 objects on one B200.
-* N > 1 (default ``--config c5``, launched by torchrun): BASELINE.json configs[4], ONE fixed 10^7-object set, each rank
-  generates and featurises its contiguous range (strong scaling), no collective during compute, ONE NCCL all-gather of
-  the concatenated float64 table at the end of each step.
+* N > 1 (default ``--config c5``, launched by torchrun): BASELINE.json configs[4], ONE fixed 10^7-object set.  Each rank
+  owns a contiguous range of the set (10^7 / N objects) and works through it in batches of 1.25 x 10^6 objects: a step is
+  one batch on every rank (N x 1.25 x 10^6 objects of the set, no collective during compute, ONE NCCL all-gather of the
+  step's float64 rows into their place in the full 10^7-row table every rank holds), so 8 / N steps make one pass over
+  the whole set and a step costs the same at every N -- the driver's ``--steps 20 --warmup 5`` stays inside its time
+  limit at N = 2 (a step over the whole set would be 53 s there).  ``config.set_passes_timed`` says how many passes over
+  the fixed set the timed steps made, ``config.seconds_per_set_pass`` is the strong-scaling reading of the same number.
 * ``--config c1|c2|c3``: the 10,178-object configs through the DataFrame-in / DataFrame-out API with the host / device
   split (c1 statistics + Bazin, c2 the 2-D GP, c3 power law + the full table).
 * ``value``  objects/s, inputs resident in HBM when the clock starts; ``e2e`` the same through the C-ABI with HOST buffers
@@ -45,6 +49,7 @@ METRIC = "light curves/sec for the 222-feature set (full 434-column module table
 UNIT = "objects/s"
 BASE_SEED = 20260118           # seed = 20260118 + config index
 C5_OBJECTS = 10_000_000
+C5_BATCH_PER_GPU = 1_250_000     # one eighth of the C5 set: what one GPU takes per step (the whole shard at N = 8)
 # ncu --set full captures of THIS build's kernels (profiles/r02_*.txt), per object; see profiles/README.md
 NCU = {"stat_dram_bytes_per_object": None, "stat_source": None, "fits": None}
 try:
@@ -279,20 +284,27 @@ def run_reference_arm(args):
     }))
 
 
-def workload_config(name, world, n_total, n_local, modules, n_rows):
+def workload_config(name, world, n_total, n_local, modules, n_rows, n_batches=1, objects_per_step=None, steps=0, step_s=0.0):
+    extra = {}
     if name == "c5":
         label = (f"C5: one fixed {n_total}-object LSST-scale synthetic set sharded over {world} B200 (BASELINE.json configs[4]); "
-                 f"each rank generates and featurises its contiguous range, one all-gather of the float64 table")
+                 f"each rank owns a contiguous range of {n_local} objects and featurises it {n_batches} batch(es) of "
+                 f"~{-(-n_local // n_batches)} objects at a time: a step = one batch on every rank + one all-gather of its float64 "
+                 f"rows into the full table; {n_batches} step(s) = one pass over the whole set")
+        extra = {"steps_per_set_pass": n_batches, "set_passes_timed": steps / n_batches,
+                 "seconds_per_set_pass": step_s * n_batches, "objects_per_step": objects_per_step}
     elif n_total == 1_000_000:
         label = "C4: 1M-object LSST-like synthetic set, full feature table (BASELINE.json configs[3])"
     else:
         label = f"C4 generator at {n_total} objects (BASELINE.json configs[3] shape)"
-    return {"workload": label, "objects_total": n_total, "objects_this_rank": n_local, "bands": 6, "mean_obs_per_object": 150,
-            "modules": list(modules), "columns": sum(MODULE_WIDTH[m] for m in modules),
-            "l2": "inputs larger than L2 (no flush needed)" if n_rows * 25 > 2 * 126e6 else "L2 flushed between steps",
-            "parallelism": f"objects sharded over {world} GPU(s) (shard.featurise_sharded), one NCCL all-gather of the "
-                           f"[objects, {sum(MODULE_WIDTH[m] for m in modules)}] float64 table" if world > 1 else
-                           "one GPU (shard.featurise_shard)"}
+    cfg = {"workload": label, "objects_total": n_total, "objects_this_rank": n_local, "bands": 6, "mean_obs_per_object": 150,
+           "modules": list(modules), "columns": sum(MODULE_WIDTH[m] for m in modules),
+           "l2": "inputs larger than L2 (no flush needed)" if n_rows * 25 > 2 * 126e6 else "L2 flushed between steps",
+           "parallelism": f"objects sharded over {world} GPU(s) (shard.featurise_shard per rank + shard.allgather_table), one NCCL "
+                          f"all-gather of the step's [objects, {sum(MODULE_WIDTH[m] for m in modules)}] float64 rows" if world > 1 else
+                          "one GPU (shard.featurise_shard)"}
+    cfg.update(extra)
+    return cfg
 
 
 # ----------------------------------------------------------------------------------------------
@@ -332,17 +344,22 @@ def run_gpu_arm(args):
         seed = (BASE_SEED + 3) * 131
     ranges = shard.equal_ranges(n_total, world)
     lo, hi = ranges[rank]
-    n_obj = hi - lo
-    cols = make_shard_columns_device(n_total, lo, hi, seed, dev)            # this rank's objects of the ONE set, in HBM
-    n_rows = int(cols["obj"].shape[0])
+    # batches of this rank's range: C5 works through the range 1.25 x 10^6 objects at a time (module docstring), C4 is one batch
+    sub = shard.batch_ranges(ranges, (args.batch_objects or C5_BATCH_PER_GPU) if config == "c5" else max(n_total, 1))   # sub[rank][batch]
+    n_batches = len(sub[0])
+    batch_rows = [[y - x for x, y in (sub[r][j] for r in range(world))] for j in range(n_batches)]   # rows_per_rank of step j
+    batches = [make_shard_columns_device(n_total, x, y, seed, dev) for x, y in sub[rank]]            # this rank's objects of the ONE set, in HBM
+    n_obj_max = max(y - x for x, y in sub[rank])
+    n_rows = max(int(c["obj"].shape[0]) for c in batches)
+    n_rows_all = sum(int(c["obj"].shape[0]) for c in batches)
     stream = torch.cuda.current_stream()
     sptr = stream.cuda_stream
     width = shard.table_width(modules)
-    table = torch.empty((n_obj, width), dtype=torch.float64, device=dev)
-    rows_per_rank = [b - a for a, b in ranges]
-    gathered = torch.empty((world * max(rows_per_rank), width), dtype=torch.float64, device=dev) if world > 1 else None
-    gp_status = torch.zeros((n_obj, 4), dtype=torch.int32, device=dev) if "gp2d" in modules else None
-    status = {"gp2d": gp_status} if gp_status is not None else {}
+    table_buf = torch.empty((n_obj_max, width), dtype=torch.float64, device=dev)
+    # the full table of the set on every rank, batch-major: block j holds [rank 0's batch j | rank 1's batch j | ...]
+    gathered = [torch.empty((world * max(batch_rows[j]), width), dtype=torch.float64, device=dev)
+                for j in range(n_batches)] if world > 1 else None
+    gp_status = [torch.zeros((y - x, 4), dtype=torch.int32, device=dev) for x, y in sub[rank]] if "gp2d" in modules else None
     flush = None
     if n_rows * 25 < 2 * 126e6:
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -351,20 +368,26 @@ def run_gpu_arm(args):
     pass_ms = {m: 0.0 for m in modules}
     pass_ms["pack"] = 0.0
     pass_ms["allgather"] = 0.0
+    timed_batches = [0] * n_batches                  # how often each batch was inside the timed region
 
-    def step(timed: bool):
+    def step(k: int, timed: bool):
+        j = k % n_batches
+        cols, (x, y) = batches[j], sub[rank][j]
         marks = [("start", ev())]
         marks[0][1].record(stream)
 
         def mark(name):
             e = ev(); e.record(stream); marks.append((name, e))
 
-        shard.featurise_shard(cols, n_obj, modules, table=table, device=local, stream=sptr, status=status, on_pass=mark)
+        table = table_buf[: y - x]
+        shard.featurise_shard(cols, y - x, modules, table=table, device=local, stream=sptr,
+                              status={"gp2d": gp_status[j]} if gp_status is not None else {}, on_pass=mark)
         if world > 1:
-            shard.allgather_table(table, rows_per_rank, out=gathered)
+            shard.allgather_table(table, batch_rows[j], out=gathered[j])
             mark("allgather")
         stream.synchronize()
         if timed:
+            timed_batches[j] += 1
             for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
                 pass_ms[name] = pass_ms.get(name, 0.0) + a.elapsed_time(b)      # 'bazin+powerlaw': the two fit passes run as one overlapped call (mlrn_fits)
 
@@ -373,17 +396,17 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step(False)
+    for k in range(args.warmup):
+        step(k, False)
     launches0 = L.mlrn_launch_count()
     barrier()
     with ClockSampler(local) as clk:
         t_start, t_end = ev(), ev()
         t_start.record(stream)
-        for _ in range(args.steps):
+        for k in range(args.steps):
             if flush is not None:
                 flush.zero_()
-            step(True)
+            step(args.warmup + k, True)
         t_end.record(stream)
         barrier()
     launches = L.mlrn_launch_count() - launches0
@@ -392,8 +415,10 @@ def run_gpu_arm(args):
         tms = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms = float(tms.item())
-    value = n_total * args.steps / (ms * 1e-3)
+    objects_timed = sum(timed_batches[j] * sum(batch_rows[j]) for j in range(n_batches))      # all ranks
+    value = objects_timed / (ms * 1e-3)
     step_s = ms * 1e-3 / args.steps
+    cols, n_obj = batches[0], sub[rank][0][1] - sub[rank][0][0]      # the legs beside the step use this rank's first batch
 
     # ---- section 8(f) row measured beside the step: the per-band 1-D GP pass (extract_gp_features), on a bounded slice
     widened = None
@@ -401,10 +426,10 @@ def run_gpu_arm(args):
         from mallorn_astrophysics_b200.store import LightCurveStore
         k = min(n_obj, args.gp1d_objects)
         keep = cols["obj"] < k
-        sub = {c: cols[c][keep].contiguous() for c in ("obj", "band", "t", "flux", "err")}
+        sl = {c: cols[c][keep].contiguous() for c in ("obj", "band", "t", "flux", "err")}
         o1 = torch.empty((k, _native.COLS["gp1d"]), dtype=torch.float64, device=dev)
         s1 = torch.zeros((k, 12), dtype=torch.int32, device=dev)
-        st1 = LightCurveStore(sub["obj"], sub["band"], sub["t"], sub["flux"], sub["err"], k, device=local, stream=sptr)
+        st1 = LightCurveStore(sl["obj"], sl["band"], sl["t"], sl["flux"], sl["err"], k, device=local, stream=sptr)
         st1.features("gp1d", out=o1, status=s1)                       # warm-up
         a, b = ev(), ev()
         a.record(stream)
@@ -418,8 +443,8 @@ def run_gpu_arm(args):
         widened = {"gp1d": {"reference": "extract_gp_features (gaussian_process.py:251), 21 columns", "objects": k,
                             "ms": gms, "objects_per_s": k / (gms * 1e-3), "bands_fitted": fitted,
                             "objective_evaluations": evals, "evaluations_per_s": evals / (gms * 1e-3),
-                            "observations": int(sub["obj"].shape[0]), "launches": 1}}
-        del sub, o1, s1
+                            "observations": int(sl["obj"].shape[0]), "launches": 1}}
+        del sl, o1, s1
 
     # ---- end to end: host buffers through the C-ABI, copies inside the timed region
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
@@ -429,7 +454,11 @@ def run_gpu_arm(args):
     host = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v) for k, v in cols.items()}
     hnp = {k: v.numpy() for k, v in host.items()}
     torch.cuda.synchronize()
+    batch_shapes = [(int(c["obj"].shape[0]), y - x) for c, (x, y) in zip(batches, sub[rank])]       # (observations, objects) per batch
     cols = None                                        # the device-resident inputs are not needed any more (big shards: 20+ GB)
+    batches.clear()
+    table = table_buf[:n_obj]
+    rows_per_rank = batch_rows[0]
     htable = torch.empty((n_obj, width), dtype=torch.float64, pin_memory=True)
     h2d = sum(hnp[k].nbytes for k in ("obj", "band", "t", "flux", "err")) + (hnp["z"].nbytes if "physics" in modules else 0)
     d2h = htable.numel() * 8
@@ -437,7 +466,7 @@ def run_gpu_arm(args):
     def e2e_step():
         shard.featurise_shard(hnp, n_obj, modules, table=table, device=local, stream=sptr)
         if world > 1:
-            shard.allgather_table(table, rows_per_rank, out=gathered)
+            shard.allgather_table(table, rows_per_rank, out=gathered[0])
         htable.copy_(table, non_blocking=True)
         stream.synchronize()
 
@@ -453,7 +482,7 @@ def run_gpu_arm(args):
         tms = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         e2e_s = float(tms.item())
-    e2e_value = n_total * e2e_steps / e2e_s
+    e2e_value = sum(rows_per_rank) * e2e_steps / e2e_s
     del host, hnp, htable
 
     if rank == 0:
@@ -467,14 +496,17 @@ def run_gpu_arm(args):
         stat_ms = pass_ms["statistical"] / args.steps if "statistical" in modules else None
         roof = None
         if stat_ms:
-            ach = algorithmic_bytes(n_rows, n_obj) / (stat_ms * 1e-3) / 1e9
+            # per launch = averaged over the timed steps (C5: the batches differ by a few objects)
+            alg = sum(timed_batches[j] * algorithmic_bytes(*batch_shapes[j]) for j in range(n_batches)) / args.steps
+            obj_per_launch = sum(timed_batches[j] * batch_shapes[j][1] for j in range(n_batches)) / args.steps
+            ach = alg / (stat_ms * 1e-3) / 1e9
             per_obj = NCU.get("stat_dram_bytes_per_object")
             roof = {"kernel": "k_stat_warp (moment pass, stat_warp.cuh / stat_fast.cu)", "bound": "hbm", "achieved": ach, "peak": peak,
                     "unit": "GB/s", "frac": ach / peak,
-                    "traffic": per_obj * n_obj if per_obj else None,
+                    "traffic": per_obj * obj_per_launch if per_obj else None,
                     "traffic_source": NCU.get("stat_source"),
                     "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s",
-                    "algorithmic_bytes_per_launch": algorithmic_bytes(n_rows, n_obj), "ms_per_launch": stat_ms}
+                    "algorithmic_bytes_per_launch": alg, "ms_per_launch": stat_ms}
         roof_gp = None
         if gp_status is not None and pass_ms.get("gp2d"):
             # dominant kernel of the step: FP64 work of the GP = evaluations x N^3 flop
@@ -483,9 +515,13 @@ def run_gpu_arm(args):
             dfma, dmma = ctypes.c_double(0.0), ctypes.c_double(0.0)
             rc = L.mlrn_measure_fp64(local, ctypes.byref(dfma), ctypes.byref(dmma))
             fp64_peak = max(dfma.value, dmma.value) if rc == 0 and max(dfma.value, dmma.value) > 0 else 37.1
-            stt = gp_status.to(torch.float64)
-            fitted = stt[:, 3] >= 10
-            flop = float(((stt[:, 1] * stt[:, 3] ** 3)[fitted]).sum())      # nfev evaluations (the one at the optimum is normally not repeated)
+            flop, stt, fitted = 0.0, None, None
+            for j in range(n_batches):                                  # per launch = averaged over the timed steps
+                if timed_batches[j]:
+                    stt = gp_status[j].to(torch.float64)
+                    fitted = stt[:, 3] >= 10
+                    flop += timed_batches[j] * float(((stt[:, 1] * stt[:, 3] ** 3)[fitted]).sum())      # nfev evaluations (the one at the optimum is normally not repeated)
+            flop /= args.steps
             gp_ms = pass_ms["gp2d"] / args.steps
             ach_tf = flop / (gp_ms * 1e-3) / 1e12
             roof_gp = {"kernel": "k_gp2d (2-D GP)", "bound": "tensor", "achieved": ach_tf, "peak": fp64_peak,
@@ -513,16 +549,17 @@ def run_gpu_arm(args):
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong" if config == "c5" else "weak",
+            "scaling": "weak",                     # per-GPU work per step is fixed as N grows (C4: 10^6 objects; C5: 1.25 x 10^6 of the set)
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(config, world, n_total, n_obj, modules, n_rows),
+            "config": workload_config(config, world, n_total, hi - lo, modules, n_rows, n_batches=n_batches,
+                                      objects_per_step=objects_timed / args.steps, steps=args.steps, step_s=step_s),
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "call": "shard.featurise_shard(host columns) + all-gather + D2H of this rank's table"},
             "gpu_launches": int(launches),
             "roofline": roof, "roofline_dominant": roof_gp, "roofline_fits": NCU.get("fits"), "cpu_baseline": cpu,
             "passes": {k: {"ms_per_step": v / args.steps, "share": v / ms} for k, v in pass_ms.items() if v > 0},
-            "observations_this_rank": n_rows,
+            "observations_this_rank": n_rows_all, "observations_this_rank_per_step": n_rows,
             "widened": widened,
         }
         print(json.dumps(out))
@@ -601,6 +638,8 @@ def main():
                     help="default: c4 on one GPU, c5 under torchrun")
     ap.add_argument("--objects", type=int, default=0,
                     help="c4: objects per GPU (default 10^6); c5: objects of the whole set (default 10^7); c1-c3: objects (default 10,178)")
+    ap.add_argument("--batch-objects", type=int, default=0,
+                    help="c5: objects one GPU takes per step (default 1.25 x 10^6 = an eighth of the set)")
     ap.add_argument("--modules", default="", help="comma list; default = every pass of the 434-column table")
     ap.add_argument("--cpu-objects", type=int, default=0, help="CPU sample size (default scales with host cores)")
     ap.add_argument("--full-cpu", action="store_true", help="c1-c3: run the CPU oracle on the whole set (minutes)")

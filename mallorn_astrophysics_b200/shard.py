@@ -61,6 +61,18 @@ def equal_ranges(n_obj: int, world: int) -> List[Tuple[int, int]]:
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
+def batch_ranges(ranges: Sequence[Tuple[int, int]], per_batch: int) -> List[List[Tuple[int, int]]]:
+    """Split every rank's contiguous range into the SAME number of contiguous batches of at most ``per_batch`` objects
+    (the tallest range decides the number): ``out[rank][batch] = (lo, hi)``.  A set too large to featurise in one go is
+    worked through batch by batch, batch ``j`` on every rank at the same time, with the all-gather of batch ``j``'s rows
+    after it; every object is in exactly one batch."""
+    if per_batch <= 0:
+        raise ValueError("per_batch must be positive")
+    tallest = max((b - a for a, b in ranges), default=0)
+    n_batches = max(1, -(-tallest // per_batch))
+    return [[(a + x, a + y) for x, y in equal_ranges(b - a, n_batches)] for a, b in ranges]
+
+
 def table_width(modules: Sequence[str]) -> int:
     from . import _native
     return sum(_native.COLS[m] for m in modules)

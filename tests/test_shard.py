@@ -131,3 +131,22 @@ def test_featurise_sharded_two_gpus_nccl():
         assert np.array_equal(got[r][0], single, equal_nan=True)        # cost-balanced ranges: bit-identical to one GPU
         assert np.array_equal(got[r][1], single, equal_nan=True)        # generator source, equal ranges
     assert got[0][3] == got[1][3] and got[0][3][0][1] != got[0][4][0][1] or True
+
+
+def test_batch_ranges_cover_every_object_once_with_equal_batch_counts():
+    """The C5 bench plan (bench.py): 10^7 objects over 2 / 4 / 8 ranks in batches of 1.25 x 10^6 -> 4 / 2 / 1 steps per pass
+    over the set, the same per-GPU batch at every N; ragged sets still partition exactly."""
+    from mallorn_astrophysics_b200.shard import batch_ranges, equal_ranges
+    for world, want in ((2, 4), (4, 2), (8, 1)):
+        sub = batch_ranges(equal_ranges(10_000_000, world), 1_250_000)
+        assert len(sub) == world and all(len(r) == want for r in sub)
+        assert all(y - x == 1_250_000 for r in sub for x, y in r)
+    for n, world, per in ((10, 3, 2), (1001, 4, 100), (5, 8, 3), (0, 2, 4)):
+        sub = batch_ranges(equal_ranges(n, world), per)
+        assert len({len(r) for r in sub}) == 1
+        flat = [i for r in sub for x, y in r for i in range(x, y)]
+        assert flat == list(range(n))
+        assert all(y - x <= per for r in sub for x, y in r)
+    import pytest
+    with pytest.raises(ValueError):
+        batch_ranges([(0, 4)], 0)
