@@ -39,6 +39,23 @@ const int64_t* mlrn_table_id_offsets(const mlrn_table* t);   /* [objects + 1] */
 const char* mlrn_table_id_chars(const mlrn_table* t);
 void mlrn_table_free(mlrn_table* t);
 
+
+/* Factorisation of a DataFrame's string columns without Python objects: the host half of every extractor's
+ * `lightcurves.groupby('object_id')` (statistical.py:155, colors.py:365, ...) and `Filter == band` masks (statistical.py:170)
+ * when the caller hands over a pandas frame whose strings are Arrow-backed (pandas >= 3 default).  A column is given as
+ * its Arrow arrays ("chunks", in row order): chunk c covers logical elements array_offset[c] .. array_offset[c]+length[c]
+ * of its buffers -- `offsets` (int32 for string, int64 for large_string: offset_bytes 4 / 8), `data` (UTF-8 bytes) and
+ * `validity` (bitmap, LSB first; the array of pointers or single entries may be NULL = no nulls).
+ * mlrn_factorize_utf8: codes[row] = dense code of the row's string numbered by first appearance over all rows
+ * (== pandas.factorize(sort=False)), -1 for a null; first_row[k] = row of the first appearance of code k (capacity: rows);
+ * *n_unique = number of codes.  Threads over row ranges with a serial merge of the ranges' distinct strings.
+ * mlrn_band_codes_utf8: band[row] = 0..5 for "u" "g" "r" "i" "z" "y", 6 for anything else or a null. */
+int mlrn_factorize_utf8(int n_chunks, const void* const* offsets, const uint8_t* const* data, const uint8_t* const* validity,
+                        const int64_t* array_offset, const int64_t* length, int offset_bytes, int n_threads,
+                        int32_t* codes, int64_t* first_row, int32_t* n_unique);
+int mlrn_band_codes_utf8(int n_chunks, const void* const* offsets, const uint8_t* const* data, const uint8_t* const* validity,
+                         const int64_t* array_offset, const int64_t* length, int offset_bytes, int n_threads, uint8_t* band);
+
 #ifdef __cplusplus
 }
 #endif

@@ -181,12 +181,30 @@ std::string_view strip(std::string_view s) {
 
 // id string -> dense code: open addressing, power-of-two capacity, the 64-bit hash kept beside the key so that a probe
 // compares one word before touching the string (std::unordered_map spent half of the parse time here)
+inline uint64_t load8(const char* p) { uint64_t w; memcpy(&w, p, 8); return w; }
 inline uint64_t hash_bytes(const char* p, size_t n) {
   uint64_t h = 0x9E3779B97F4A7C15ull ^ (n * 0xff51afd7ed558ccdull);
-  while (n >= 8) { uint64_t w; memcpy(&w, p, 8); h = (h ^ w) * 0x9FB21C651E98DF25ull; h ^= h >> 29; p += 8; n -= 8; }
-  uint64_t w = 0; memcpy(&w, p, n);
-  h = (h ^ w) * 0x9FB21C651E98DF25ull;
-  return h ^ (h >> 32);
+  if (n >= 8) {                                     // whole words, then the last eight bytes again (overlapping): no variable-length copy
+    const char* last = p + n - 8;
+    for (; p < last; p += 8) { h = (h ^ load8(p)) * 0x9FB21C651E98DF25ull; h ^= h >> 29; }
+    h = (h ^ load8(last)) * 0x9FB21C651E98DF25ull;
+  } else {
+    uint64_t w = 0;
+    for (size_t k = 0; k < n; ++k) w |= (uint64_t)(unsigned char)p[k] << (8 * k);
+    h = (h ^ w) * 0x9FB21C651E98DF25ull;
+  }
+  // full avalanche (the varying digits of an id sit in the HIGH bytes of the last word; a table index is the LOW bits)
+  h ^= h >> 33; h *= 0xff51afd7ed558ccdull; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 33;
+  return h;
+}
+inline bool same_bytes(const char* a, const char* b, size_t n) {      // n is the same for both
+  if (n >= 8) {
+    const char* last = a + n - 8;
+    for (; a < last; a += 8, b += 8) if (load8(a) != load8(b)) return false;
+    return load8(last) == load8(b + (last - a));
+  }
+  for (size_t k = 0; k < n; ++k) if (a[k] != b[k]) return false;
+  return true;
 }
 struct IdTable {
   struct Slot { uint64_t h; uint32_t off; uint32_t n; int32_t code; };      // code < 0: empty
@@ -201,7 +219,10 @@ struct IdTable {
   }
   // returns the code of `id`, inserting it with `next_code` if new (then inserted = true)
   int32_t find_or_insert(std::string_view id, int32_t next_code, bool& inserted) {
-    const uint64_t h = hash_bytes(id.data(), id.size());
+    return find_or_insert(id, hash_bytes(id.data(), id.size()), next_code, inserted);
+  }
+  void prefetch(uint64_t h) const { __builtin_prefetch(&slots[h & (slots.size() - 1)]); }
+  int32_t find_or_insert(std::string_view id, uint64_t h, int32_t next_code, bool& inserted) {
     size_t i = h & (slots.size() - 1);
     for (;;) {
       Slot& s = slots[i];
@@ -212,7 +233,7 @@ struct IdTable {
         if (++used * 2 > slots.size()) grow();
         return next_code;
       }
-      if (s.h == h && s.n == id.size() && memcmp(arena.data() + s.off, id.data(), id.size()) == 0) { inserted = false; return s.code; }
+      if (s.h == h && s.n == id.size() && same_bytes(arena.data() + s.off, id.data(), id.size())) { inserted = false; return s.code; }
       i = (i + 1) & (slots.size() - 1);
     }
   }
@@ -417,6 +438,115 @@ int mlrn_ingest_csv(const char* const* paths, int n_paths, int n_threads, mlrn_t
     }
   });
   *out = tb;
+  return MLRN_INGEST_OK;
+}
+
+// ---- factorisation of an Arrow string column (include/mallorn_ingest.h) -------------------------------------------------
+namespace {
+struct Utf8Chunk {                   // one Arrow (large_)string array: rows [0, n) are logical rows offset .. offset+n of its buffers
+  const void* offsets; const char* data; const uint8_t* validity; int64_t offset, n, row0; int width;
+  inline bool valid(int64_t i) const { const int64_t k = offset + i; return !validity || ((validity[k >> 3] >> (k & 7)) & 1); }
+  inline std::string_view at(int64_t i) const {
+    const int64_t k = offset + i;
+    if (width == 8) { const int64_t* o = (const int64_t*)offsets; return std::string_view(data + o[k], (size_t)(o[k + 1] - o[k])); }
+    const int32_t* o = (const int32_t*)offsets; return std::string_view(data + o[k], (size_t)(o[k + 1] - o[k]));
+  }
+};
+struct Utf8Job { int chunk; int64_t lo, hi; std::vector<std::string_view> local_ids; std::vector<int64_t> local_first; std::vector<int32_t> local_to_global; };
+
+bool utf8_chunks(int n_chunks, const void* const* offsets, const uint8_t* const* data, const uint8_t* const* validity,
+                 const int64_t* array_offset, const int64_t* length, int offset_bytes, std::vector<Utf8Chunk>& out, int64_t& rows) {
+  if (n_chunks < 0 || (offset_bytes != 4 && offset_bytes != 8)) return false;
+  rows = 0;
+  for (int c = 0; c < n_chunks; ++c) {
+    if (length[c] < 0 || array_offset[c] < 0 || (length[c] > 0 && (!offsets[c]))) return false;
+    out.push_back(Utf8Chunk{offsets[c], (const char*)data[c], validity ? validity[c] : nullptr, array_offset[c], length[c], rows, offset_bytes});
+    rows += length[c];
+  }
+  return rows <= 0x7fffffffLL;
+}
+}  // namespace
+
+int mlrn_factorize_utf8(int n_chunks, const void* const* offsets, const uint8_t* const* data, const uint8_t* const* validity,
+                        const int64_t* array_offset, const int64_t* length, int offset_bytes, int n_threads,
+                        int32_t* codes, int64_t* first_row, int32_t* n_unique) {
+  std::vector<Utf8Chunk> chunks; int64_t rows = 0;
+  if (!codes || !first_row || !n_unique || !utf8_chunks(n_chunks, offsets, data, validity, array_offset, length, offset_bytes, chunks, rows)) {
+    g_err = "mlrn_factorize_utf8: bad argument (or more than 2^31-1 rows)"; return MLRN_INGEST_EINVAL;
+  }
+  if (n_threads <= 0) { n_threads = (int)std::thread::hardware_concurrency(); if (n_threads <= 0) n_threads = 1; }
+  // jobs: contiguous row ranges inside one chunk, about rows / n_threads each (few jobs: every job's distinct ids are merged serially)
+  const int64_t per = std::max<int64_t>(16384, (rows + n_threads - 1) / n_threads);
+  std::vector<Utf8Job> jobs;
+  for (int c = 0; c < n_chunks; ++c)
+    for (int64_t lo = 0; lo < chunks[(size_t)c].n; lo += per) jobs.push_back(Utf8Job{c, lo, std::min(lo + per, chunks[(size_t)c].n), {}, {}, {}});
+  try {
+    run_parallel((int)jobs.size(), n_threads, [&](int j) {
+      Utf8Job& job = jobs[(size_t)j];
+      const Utf8Chunk& ch = chunks[(size_t)job.chunk];
+      IdTable local;
+      std::string_view prev; int32_t prev_code = -1;
+      constexpr int BLOCK = 16;                     // hashes of a block first, with a prefetch of each slot: the probes of a shuffled
+      uint64_t hs[BLOCK];                           // file are cache misses, and a mispredicted probe branch serialises them otherwise
+      for (int64_t b0 = job.lo; b0 < job.hi; b0 += BLOCK) {
+        const int nb = (int)std::min<int64_t>(BLOCK, job.hi - b0);
+        for (int k = 0; k < nb; ++k)
+          if (ch.valid(b0 + k)) { const std::string_view id = ch.at(b0 + k); hs[k] = hash_bytes(id.data(), id.size()); local.prefetch(hs[k]); }
+        for (int k = 0; k < nb; ++k) {
+          const int64_t i = b0 + k;
+          int32_t code = -1;
+          if (ch.valid(i)) {
+            const std::string_view id = ch.at(i);
+            if (prev_code >= 0 && id.size() == prev.size() && same_bytes(id.data(), prev.data(), id.size())) code = prev_code;     // files grouped by object
+            else {
+              bool fresh = false;
+              code = local.find_or_insert(id, hs[k], (int32_t)job.local_ids.size(), fresh);
+              if (fresh) { job.local_ids.push_back(id); job.local_first.push_back(ch.row0 + i); }
+              prev = id; prev_code = code;
+            }
+          }
+          codes[(size_t)(ch.row0 + i)] = code;
+        }
+      }
+    });
+    // global codes in order of first appearance over all rows (== pandas.factorize(sort=False)): jobs are in row order
+    IdTable global; int32_t n_glob = 0;
+    for (auto& job : jobs) {
+      job.local_to_global.resize(job.local_ids.size());
+      for (size_t k = 0; k < job.local_ids.size(); ++k) {
+        bool fresh = false;
+        const int32_t gid = global.find_or_insert(job.local_ids[k], n_glob, fresh);
+        if (fresh) { first_row[(size_t)n_glob] = job.local_first[k]; ++n_glob; }
+        job.local_to_global[k] = gid;
+      }
+    }
+    run_parallel((int)jobs.size(), n_threads, [&](int j) {
+      const Utf8Job& job = jobs[(size_t)j];
+      const int64_t r0 = chunks[(size_t)job.chunk].row0;
+      for (int64_t r = r0 + job.lo; r < r0 + job.hi; ++r) { const int32_t lc = codes[(size_t)r]; if (lc >= 0) codes[(size_t)r] = job.local_to_global[(size_t)lc]; }
+    });
+    *n_unique = n_glob;
+  } catch (const std::bad_alloc&) { g_err = "mlrn_factorize_utf8: out of memory"; return MLRN_INGEST_EIO; }
+  return MLRN_INGEST_OK;
+}
+
+int mlrn_band_codes_utf8(int n_chunks, const void* const* offsets, const uint8_t* const* data, const uint8_t* const* validity,
+                         const int64_t* array_offset, const int64_t* length, int offset_bytes, int n_threads, uint8_t* band) {
+  std::vector<Utf8Chunk> chunks; int64_t rows = 0;
+  if (!band || !utf8_chunks(n_chunks, offsets, data, validity, array_offset, length, offset_bytes, chunks, rows)) {
+    g_err = "mlrn_band_codes_utf8: bad argument (or more than 2^31-1 rows)"; return MLRN_INGEST_EINVAL;
+  }
+  if (n_threads <= 0) { n_threads = (int)std::thread::hardware_concurrency(); if (n_threads <= 0) n_threads = 1; }
+  struct Job { int chunk; int64_t lo, hi; };
+  const int64_t per = std::max<int64_t>(65536, (rows + n_threads - 1) / n_threads);
+  std::vector<Job> jobs;
+  for (int c = 0; c < n_chunks; ++c)
+    for (int64_t lo = 0; lo < chunks[(size_t)c].n; lo += per) jobs.push_back(Job{c, lo, std::min(lo + per, chunks[(size_t)c].n)});
+  run_parallel((int)jobs.size(), n_threads, [&](int j) {
+    const Job& job = jobs[(size_t)j];
+    const Utf8Chunk& ch = chunks[(size_t)job.chunk];
+    for (int64_t i = job.lo; i < job.hi; ++i) band[(size_t)(ch.row0 + i)] = ch.valid(i) ? band_code(ch.at(i)) : (uint8_t)6;
+  });
   return MLRN_INGEST_OK;
 }
 

@@ -45,6 +45,10 @@ def lib() -> C.CDLL:
                      "mlrn_table_free"):
             getattr(L, name).argtypes = [vp]
         L.mlrn_table_free.restype = None
+        pp = C.POINTER(vp)
+        chunk_args = [C.c_int, pp, pp, pp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int, C.c_int]
+        L.mlrn_factorize_utf8.argtypes = chunk_args + [vp, vp, C.POINTER(C.c_int32)]
+        L.mlrn_band_codes_utf8.argtypes = chunk_args + [vp]
         _lib = L
     return _lib
 
@@ -95,6 +99,83 @@ def _view(owner: _Table, ptr, n: int, dtype) -> np.ndarray:
     buf = (np.ctypeslib.as_ctypes_type(dtype) * n).from_address(ptr)
     buf._owner = owner                               # ctypes instances accept attributes; numpy keeps `buf` as .base
     return np.frombuffer(buf, dtype=dtype)
+
+
+def _arrow_string_chunks(column):
+    """The Arrow arrays behind a pandas string column (``str`` / ``string[pyarrow]`` / ``ArrowDtype(string)``), or ``None``
+    when the column is not Arrow-backed UTF-8 (object dtype, python-backed strings, categoricals ...)."""
+    arr = getattr(column, "array", column)
+    if not hasattr(arr, "__arrow_array__"):
+        return None
+    dt = getattr(arr, "dtype", None)
+    if getattr(dt, "storage", None) != "pyarrow" and type(dt).__name__ != "ArrowDtype":
+        return None                                            # python-backed strings would be converted (copied) by the protocol
+    try:
+        import pyarrow as pa
+        pa_arr = arr.__arrow_array__()
+    except Exception:
+        return None
+    chunks = list(pa_arr.chunks) if isinstance(pa_arr, pa.ChunkedArray) else [pa_arr]
+    if chunks and all(pa.types.is_large_string(c.type) for c in chunks):
+        width = 8
+    elif chunks and all(pa.types.is_string(c.type) for c in chunks):
+        width = 4
+    elif chunks:
+        return None
+    else:
+        width = 8
+    return chunks, width
+
+
+def _chunk_args(chunks, width: int, threads: int):
+    n = len(chunks)
+    vp = C.c_void_p
+    offs, data, valid = (vp * max(n, 1))(), (vp * max(n, 1))(), (vp * max(n, 1))()
+    aoff, length = (C.c_int64 * max(n, 1))(), (C.c_int64 * max(n, 1))()
+    for i, c in enumerate(chunks):
+        v, o, d = c.buffers()
+        offs[i] = o.address if o is not None else None
+        data[i] = d.address if d is not None and d.size else None
+        valid[i] = v.address if v is not None and c.null_count else None
+        aoff[i], length[i] = c.offset, len(c)
+    return [n, offs, data, valid, aoff, length, width, int(threads)]
+
+
+def factorize_strings(column, threads: int = 0):
+    """``pandas.factorize(column, sort=False)`` for an Arrow-backed string column, on all host cores and without creating
+    a Python object per row: ``(codes int32 [rows] (-1 = null), uniques)`` with ``uniques`` the distinct strings in order of
+    first appearance (an object ndarray).  Returns ``None`` when the column is not Arrow-backed (the caller then uses pandas)."""
+    got = _arrow_string_chunks(column)
+    if got is None:
+        return None
+    chunks, width = got
+    rows = sum(len(c) for c in chunks)
+    codes = np.empty(rows, dtype=np.int32)
+    first = np.empty(rows, dtype=np.int64)
+    n_unique = C.c_int32(0)
+    L = lib()
+    rc = L.mlrn_factorize_utf8(*_chunk_args(chunks, width, threads), codes.ctypes.data, first.ctypes.data, C.byref(n_unique))
+    if rc != 0:
+        raise MallornIngestError(f"mlrn_factorize_utf8 failed ({rc}): {L.mlrn_ingest_last_error().decode()}")
+    import pyarrow as pa
+    whole = pa.chunked_array(chunks) if chunks else pa.chunked_array([], type=pa.large_string())
+    uniques = whole.take(pa.array(first[: n_unique.value])).to_numpy(zero_copy_only=False) if n_unique.value else np.empty(0, dtype=object)
+    return codes, np.asarray(uniques, dtype=object)
+
+
+def band_codes(column, threads: int = 0):
+    """``Filter`` strings -> uint8 band codes (0..5 = u g r i z y, 6 = anything else or null) for an Arrow-backed string
+    column; ``None`` when the column is not Arrow-backed."""
+    got = _arrow_string_chunks(column)
+    if got is None:
+        return None
+    chunks, width = got
+    band = np.empty(sum(len(c) for c in chunks), dtype=np.uint8)
+    L = lib()
+    rc = L.mlrn_band_codes_utf8(*_chunk_args(chunks, width, threads), band.ctypes.data)
+    if rc != 0:
+        raise MallornIngestError(f"mlrn_band_codes_utf8 failed ({rc}): {L.mlrn_ingest_last_error().decode()}")
+    return band
 
 
 def read_lightcurve_csv(paths: Union[str, Path, Sequence[Union[str, Path]]], threads: int = 0) -> LightCurveColumns:

@@ -59,25 +59,28 @@ def frame_columns(lightcurves, object_ids: Optional[Sequence] = None):
     ``ids`` (the unique requested ids in request order; default: order of first appearance, as
     ``lightcurves['object_id'].unique()``), -1 for rows of objects that were not requested or have no id;
     ``band[i]`` is 0..5 for u g r i z y and ``UNKNOWN_BAND`` for any other ``Filter`` value (NaN included).
-    The strings are hashed once (``pandas.factorize``) and the per-row work is integer gathers; row order is the
+    The strings are hashed once -- by ``libmallorn_ingest.so`` on all host cores straight from the Arrow buffers when the
+    frame's strings are Arrow-backed (``ingest.factorize_strings``; pandas >= 3 default), by ``pandas.factorize``
+    otherwise -- and the per-row work is integer gathers; row order is the
     file order, which K1 preserves inside each object.  Replaces the ``groupby('object_id')`` dict every
     reference extractor builds (``statistical.py:155`` ...) and the ``Filter == band`` masks.
     """
     import pandas as pd
-    row_code, uniq = pd.factorize(lightcurves["object_id"], sort=False)          # -1 for a missing id
+    from . import ingest
+    fast = ingest.factorize_strings(lightcurves["object_id"])                    # Arrow-backed strings (pandas >= 3): native, all cores
+    row_code, uniq = fast if fast is not None else pd.factorize(lightcurves["object_id"], sort=False)      # -1 for a missing id
     if object_ids is None:
         ids = pd.Index(uniq)
         remap = np.arange(len(uniq), dtype=np.int32)
     else:
         ids = pd.Index(pd.unique(pd.Series(list(object_ids), dtype=object)))
         remap = ids.get_indexer(pd.Index(uniq)).astype(np.int32)                 # -1: present in the frame, not requested
-    obj = np.full(len(row_code), -1, dtype=np.int32)
-    ok = row_code >= 0
-    if len(remap):
-        obj[ok] = remap[row_code[ok]]
-    band_code, band_uniq = pd.factorize(lightcurves["Filter"], sort=False)
-    lut = np.array([BAND_CODE.get(x, UNKNOWN_BAND) for x in band_uniq] + [UNKNOWN_BAND], dtype=np.uint8)
-    band = lut[band_code]                                                         # code -1 (NaN) -> the appended UNKNOWN entry
+    obj = np.append(remap, np.int32(-1))[row_code]                                # code -1 (no id) -> the appended -1
+    band = ingest.band_codes(lightcurves["Filter"])
+    if band is None:
+        band_code, band_uniq = pd.factorize(lightcurves["Filter"], sort=False)
+        lut = np.array([BAND_CODE.get(x, UNKNOWN_BAND) for x in band_uniq] + [UNKNOWN_BAND], dtype=np.uint8)
+        band = lut[band_code]                                                     # code -1 (NaN) -> the appended UNKNOWN entry
     return (obj, band,
             lightcurves["Time (MJD)"].to_numpy(dtype=np.float64),
             lightcurves["Flux"].to_numpy(dtype=np.float64),
