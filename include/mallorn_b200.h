@@ -11,6 +11,11 @@
  * is a cudaStream_t passed as void* (NULL = the legacy default stream).  With device outputs the
  * calls are asynchronous on `stream`; with host outputs they return after the copy completes.
  *
+ * Concurrency: a store belongs to one host thread and one stream at a time -- the passes keep their work counters in the
+ * store, so two passes on the SAME store must be ordered (same stream, or an event between them; mlrn_fits orders its
+ * own internal side stream).  Different stores are independent and may be used from different threads and streams.
+ * mlrn_last_error() is per thread.
+ *
  * Feature rows are float64, row-major [n_obj, n_cols], columns in the reference's order
  * (mallorn_astrophysics_b200/schema.py).  One row per dense object index 0..n_obj-1; an object
  * without observations yields the reference's "empty" values and is dropped by the shim
@@ -30,7 +35,8 @@ extern "C" {
 #define MLRN_ETOOLONG (-3)    /* an object has more than MLRN_MAX_OBS observations */
 #define MLRN_ENODEVICE (-4)   /* no CUDA device: there is no CPU fallback */
 
-#define MLRN_MAX_OBS 1024     /* per-object observation cap (shared-memory staging) */
+#define MLRN_MAX_OBS 65535    /* per-object observation cap: within-object file ranks are uint16.  Objects up to 512
+                               * observations are staged in shared memory, longer ones in a global scratch (same code) */
 #define MLRN_N_SEG 7          /* segments per object: u g r i z y + unknown filter */
 
 #define MLRN_STAT_COLS 123      /* extract_statistical_features   statistical.py:135      */
