@@ -19,7 +19,7 @@ MLRN_FN_FORCE double mag_color(double f1, double f2) {            // colors.py:9
 }
 
 // Linear interpolation on a time-sorted band (colors.py:47-89; numpy.searchsorted side='left').
-MLRN_FN double lerp_flux(const double* ts, const double* fs, int n, double target, double max_gap) {
+MLRN_TEAM_FN double lerp_flux(const double* ts, const double* fs, int n, double target, double max_gap) {
   if (n < 2) return qnan();
   if (target < ts[0] || target > ts[n - 1]) return qnan();
   if (is_nan(target)) return fs[n - 1];                           // searchsorted puts NaN at the end

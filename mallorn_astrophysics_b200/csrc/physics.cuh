@@ -13,7 +13,7 @@ namespace mlrn {
 constexpr int PHYSICS_COLS = 32;
 
 template <class Team>
-MLRN_FN double stetson_j(const Team& tm, const ObjView& v, int b1, int b2) {     // physics_based.py:49-82
+MLRN_TEAM_FN double stetson_j(const Team& tm, const ObjView& v, int b1, int b2) {     // physics_based.py:49-82
   const int n1 = v.cnt(b1), n2 = v.cnt(b2);
   const double *t1 = v.t + v.off[b1], *f1 = v.f + v.off[b1], *e1 = v.e + v.off[b1];
   const double *t2 = v.t + v.off[b2], *f2 = v.f + v.off[b2], *e2 = v.e + v.off[b2];
@@ -35,7 +35,7 @@ MLRN_FN double stetson_j(const Team& tm, const ObjView& v, int b1, int b2) {    
 }
 
 template <class Team>
-MLRN_FN double stetson_k(const Team& tm, const double* f, const double* e, int n) {   // :92-107
+MLRN_TEAM_FN double stetson_k(const Team& tm, const double* f, const double* e, int n) {   // :92-107
   if (n < 4) return qnan();
   double mean = team_mean(tm, f, n);
   double s1 = 0.0, s2 = 0.0; int nv = 0;
@@ -46,7 +46,7 @@ MLRN_FN double stetson_k(const Team& tm, const double* f, const double* e, int n
   return s1 / sqrt(s2) / sqrt((double)n);
 }
 
-MLRN_FN double phys_temperature(double g, double r, double i) {                  // :179-199
+MLRN_TEAM_FN double phys_temperature(double g, double r, double i) {                  // :179-199
   if (is_nan(g) || is_nan(r) || is_nan(i) || g <= 0.0 || r <= 0.0 || i <= 0.0) return qnan();
   double c = -2.5 * log10(g / r);
   double temp = (c < -0.5) ? 50000.0 : ((c > 2.0) ? 3000.0 : 7000.0 / (c + 0.6));

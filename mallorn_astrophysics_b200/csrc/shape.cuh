@@ -13,7 +13,7 @@ constexpr int SHAPE_COLS = 65;
 // Log-log decay fit shared by the band and all-band blocks (lightcurve_shape.py:107-144):
 // points with t > t_peak + 5 and f > 0, need >= 5; x = log10(max(dt, 1)), y = log10(max(f, 1e-10)).
 template <class Team>
-MLRN_FN void loglog_decay(const Team& tm, const double* t, const double* f, int n, double pt, double pf,
+MLRN_TEAM_FN void loglog_decay(const Team& tm, const double* t, const double* f, int n, double pt, double pf,
                           double* sx, double* sy, double& alpha, double& resid) {
   alpha = qnan(); resid = qnan();
   if (is_nan(pt) || is_nan(pf)) return;

@@ -12,7 +12,7 @@ namespace mlrn {
 constexpr int TDE_COLS = 25;
 
 // index of the band-2 point nearest in time (first minimum of |t2 - a|), as numpy.argmin
-MLRN_FN int nearest_first(const double* t2, int n2, double a, double& dmin) {
+MLRN_TEAM_FN int nearest_first(const double* t2, int n2, double a, double& dmin) {
   int best = 0; dmin = fabs(t2[0] - a);
   for (int j = 1; j < n2; ++j) { double d = fabs(t2[j] - a); if (d < dmin) { dmin = d; best = j; } }
   return best;
@@ -21,7 +21,7 @@ MLRN_FN int nearest_first(const double* t2, int n2, double a, double& dmin) {
 // Collects, in band-1 time order, (value, time) of the pairs that pass; value from `map`.
 // MODE 0: magnitude colour (tde_physics.py:52-66); MODE 1: temperature proxy (:234-258).
 template <int MODE, class Team>
-MLRN_FN int paired_series(const Team& tm, const ObjView& v, int b1, int b2, double window, double* vals, double* times) {
+MLRN_TEAM_FN int paired_series(const Team& tm, const ObjView& v, int b1, int b2, double window, double* vals, double* times) {
   const int n1 = v.cnt(b1), n2 = v.cnt(b2);
   const double* t1 = v.t + v.off[b1]; const double* f1 = v.f + v.off[b1];
   const double* t2 = v.t + v.off[b2]; const double* f2 = v.f + v.off[b2];
@@ -32,7 +32,7 @@ MLRN_FN int paired_series(const Team& tm, const ObjView& v, int b1, int b2, doub
     if (i < n1) {
       double d; int j = nearest_first(t2, n2, t1[i], d);
       if (d < window && f1[i] > 0.0 && f2[j] > 0.0) {
-        double c = -2.5 * log10(f1[i] / f2[j]);
+        double c = -2.5 * team_log10(f1[i] / f2[j]);
         if (MODE == 0) val = c;
         else val = (c < -0.5) ? 40000.0 : ((c > 1.5) ? 5000.0 : 7000.0 / (c + 0.5));
         keep = true;
@@ -81,7 +81,7 @@ MLRN_FN void tde_row(const Team& tm, const ObjView& v, double* sa, double* sb, d
       int i = base + tm.rank();
       bool keep = (i < n) && (t[i] > pt + 50.0);
       int slot = tm.compact_slot(keep, cnt);
-      if (keep) { sa[slot] = log10(t[i] - pt + 1.0); sb[slot] = log10(fmax(f[i], 1e-10)); sc[slot] = f[i]; }
+      if (keep) { sa[slot] = team_log10(t[i] - pt + 1.0); sb[slot] = team_log10(fmax(f[i], 1e-10)); sc[slot] = f[i]; }
     }
     tm.sync();
     if (cnt >= 3 && pf > 0.0) {
@@ -151,9 +151,10 @@ MLRN_FN void tde_row(const Team& tm, const ObjView& v, double* sa, double* sb, d
         bool late = keep && (dt > 50.0);
         npost += post ? 1 : 0;
         int slot = tm.compact_slot(keep, cnt);
-        if (keep) { sa[slot] = log10(dt); sb[slot] = log10(f[i]); }
+        double ldt = 0.0, lf = 0.0;
+        if (keep) { ldt = team_log10(dt); lf = team_log10(f[i]); sa[slot] = ldt; sb[slot] = lf; }
         int sl = tm.compact_slot(late, cl);
-        if (late) { sc[sl] = log10(dt); sd[sl] = log10(f[i]); }
+        if (late) { sc[sl] = ldt; sd[sl] = lf; }                    // late implies keep: the same two logarithms
       }
       npost = tm.isum(npost);
       tm.sync();

@@ -21,7 +21,19 @@
 #define MLRN_HD __host__ __device__ inline
 #define MLRN_ROLL _Pragma("unroll 1")     // keep the NP-sized loops of the solver rolled (code size)
 #define MLRN_NOINLINE __device__ __noinline__     // one copy per kernel: keeps the thread-per-fit kernels inside the i-cache
+// Team helpers (reductions, sorts, pairings): inlined by default; a translation unit that defines MLRN_SHARED_HELPERS
+// before including this header gets ONE copy of each per module instead.  passes.cu does: the K3 rows call them 40-75 times
+// each, and inlined the kernels were 6-13 k instructions (100-200 KB of code against a 128 KB instruction cache).
+#ifdef MLRN_SHARED_HELPERS
+#define MLRN_TEAM_FN __device__ __noinline__
+#define MLRN_TEAM_MEMBER __device__ __noinline__
 #else
+#define MLRN_TEAM_FN __device__ inline
+#define MLRN_TEAM_MEMBER __device__
+#endif
+#else
+#define MLRN_TEAM_FN inline
+#define MLRN_TEAM_MEMBER
 #define MLRN_FN inline
 #define MLRN_FN_FORCE inline
 #define MLRN_HD inline
@@ -77,6 +89,15 @@ struct WarpTeam {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
   }
+  // two independent sums through one butterfly: the shuffles of the second chain issue under the latency of the first
+  // (each chain adds in exactly the order of sum(): bit-identical to two calls)
+  __device__ __forceinline__ void sum2(double& a, double& b) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double oa = __shfl_xor_sync(FULL, a, o), ob = __shfl_xor_sync(FULL, b, o);
+      a += oa; b += ob;
+    }
+  }
   __device__ __forceinline__ int isum(int v) const { return __reduce_add_sync(FULL, v); }
   __device__ __forceinline__ int imin(int v) const { return __reduce_min_sync(FULL, v); }
   __device__ __forceinline__ int imax(int v) const { return __reduce_max_sync(FULL, v); }
@@ -129,7 +150,7 @@ struct WarpTeam {
   }
 
   // Ascending bitonic sort of a[0..n) in shared scratch; capacity must be >= next_pow2(n).
-  __device__ void sort(double* a, int n) const {
+  MLRN_TEAM_MEMBER void sort(double* a, int n) const {
     int np = next_pow2(n);
     for (int i = n + lane_; i < np; i += 32) a[i] = pinf();
     __syncwarp();
@@ -148,7 +169,7 @@ struct WarpTeam {
     }
   }
   // Ascending sort by key with a payload; ties broken by payload order is NOT guaranteed.
-  __device__ void sort_by_key(double* key, double* val, int n) const {
+  MLRN_TEAM_MEMBER void sort_by_key(double* key, double* val, int n) const {
     int np = next_pow2(n);
     for (int i = n + lane_; i < np; i += 32) { key[i] = pinf(); val[i] = 0.0; }
     __syncwarp();
@@ -179,6 +200,7 @@ struct HostTeam {
   int rank() const { return 0; }
   void sync() const {}
   double sum(double v) const { return v; }
+  void sum2(double&, double&) const {}
   int isum(int v) const { return v; }
   int imin(int v) const { return v; }
   int imax(int v) const { return v; }
@@ -204,7 +226,7 @@ struct HostTeam {
 // Small team-wide reductions over scratch arrays (all members get the same answer).
 // ----------------------------------------------------------------------------------------------
 template <class Team>
-MLRN_FN double team_sum(const Team& tm, const double* a, int n) {
+MLRN_TEAM_FN double team_sum(const Team& tm, const double* a, int n) {
   double s = 0.0;
   for (int i = tm.rank(); i < n; i += Team::size) s += a[i];
   return tm.sum(s);
@@ -214,26 +236,26 @@ MLRN_FN double team_mean(const Team& tm, const double* a, int n) { return team_s
 
 // population variance, two-pass (numpy.var / numpy.std, ddof = 0)
 template <class Team>
-MLRN_FN double team_var(const Team& tm, const double* a, int n, double mean) {
+MLRN_TEAM_FN double team_var(const Team& tm, const double* a, int n, double mean) {
   double s = 0.0;
   for (int i = tm.rank(); i < n; i += Team::size) { double d = a[i] - mean; s += d * d; }
   return tm.sum(s) / (double)n;
 }
 template <class Team>
-MLRN_FN double team_max(const Team& tm, const double* a, int n) {
+MLRN_TEAM_FN double team_max(const Team& tm, const double* a, int n) {
   double m = -pinf();
   for (int i = tm.rank(); i < n; i += Team::size) m = fmax(m, a[i]);
   return tm.max(m);
 }
 template <class Team>
-MLRN_FN double team_min(const Team& tm, const double* a, int n) {
+MLRN_TEAM_FN double team_min(const Team& tm, const double* a, int n) {
   double m = pinf();
   for (int i = tm.rank(); i < n; i += Team::size) m = fmin(m, a[i]);
   return tm.min(m);
 }
 // first index of the maximum of a[0..n) (numpy.argmax); -1 if n == 0
 template <class Team>
-MLRN_FN int team_argmax_first(const Team& tm, const double* a, int n) {
+MLRN_TEAM_FN int team_argmax_first(const Team& tm, const double* a, int n) {
   double bv = 0.0; int bi = -1;
   for (int i = tm.rank(); i < n; i += Team::size) {
     double v = a[i];
@@ -243,7 +265,7 @@ MLRN_FN int team_argmax_first(const Team& tm, const double* a, int n) {
 }
 // first index of the minimum of a[0..n) (numpy.argmin); -1 if n == 0
 template <class Team>
-MLRN_FN int team_argmin_first(const Team& tm, const double* a, int n) {
+MLRN_TEAM_FN int team_argmin_first(const Team& tm, const double* a, int n) {
   double bv = 0.0; int bi = -1;
   for (int i = tm.rank(); i < n; i += Team::size) {
     double v = a[i];
@@ -251,6 +273,9 @@ MLRN_FN int team_argmin_first(const Team& tm, const double* a, int n) {
   }
   return tm.argmin_first(bv, bi);
 }
+
+// log10 through one shared copy where helpers are shared (13 call sites in the TDE row alone)
+MLRN_TEAM_FN double team_log10(double x) { return log10(x); }
 
 // numpy.percentile(method='linear') on an ascending-sorted array
 MLRN_FN double sorted_percentile(const double* s, int n, double q) {
@@ -268,14 +293,17 @@ MLRN_FN double sorted_median(const double* s, int n) {
 // Ordinary least squares y = a x + b (numpy.polyfit(x, y, 1) for full-rank data); centred sums.
 struct Line { double slope, icpt; };
 template <class Team>
-MLRN_FN Line team_polyfit1(const Team& tm, const double* x, const double* y, int n) {
-  double mx = team_mean(tm, x, n), my = team_mean(tm, y, n);
+MLRN_TEAM_FN Line team_polyfit1(const Team& tm, const double* x, const double* y, int n) {
+  double mx = 0.0, my = 0.0;                         // the two means, then the two centred sums: each pair in one butterfly
+  for (int i = tm.rank(); i < n; i += Team::size) { mx += x[i]; my += y[i]; }
+  tm.sum2(mx, my);
+  mx /= (double)n; my /= (double)n;
   double sxx = 0.0, sxy = 0.0;
   for (int i = tm.rank(); i < n; i += Team::size) {
     double dx = x[i] - mx;
     sxx += dx * dx; sxy += dx * (y[i] - my);
   }
-  sxx = tm.sum(sxx); sxy = tm.sum(sxy);
+  tm.sum2(sxx, sxy);
   Line l; l.slope = sxy / sxx; l.icpt = my - l.slope * mx;
   return l;
 }
