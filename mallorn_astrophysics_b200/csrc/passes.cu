@@ -5,7 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdlib.h>
 #ifndef MLRN_K3_INLINE             // developer build: the helpers inlined, as before
-#define MLRN_SHARED_HELPERS      // team.cuh: one copy of every team helper per module (instruction-cache footprint of the rows)
+#define MLRN_SHARED_HELPERS      // team.cuh: one copy of every team helper per kernel (instruction-cache footprint of the rows)
 #endif
 #include "store.cuh"
 #include "stat.cuh"

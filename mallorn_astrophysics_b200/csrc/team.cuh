@@ -22,7 +22,7 @@
 #define MLRN_ROLL _Pragma("unroll 1")     // keep the NP-sized loops of the solver rolled (code size)
 #define MLRN_NOINLINE __device__ __noinline__     // one copy per kernel: keeps the thread-per-fit kernels inside the i-cache
 // Team helpers (reductions, sorts, pairings): inlined by default; a translation unit that defines MLRN_SHARED_HELPERS
-// before including this header gets ONE copy of each per module instead.  passes.cu does: the K3 rows call them 40-75 times
+// before including this header gets ONE copy of each per kernel instead.  passes.cu does: the K3 rows call them 40-75 times
 // each, and inlined the kernels were 6-13 k instructions (100-213 KB of code against a 128 KB instruction cache).
 #ifdef MLRN_SHARED_HELPERS
 #define MLRN_TEAM_FN __device__ __noinline__

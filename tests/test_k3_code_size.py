@@ -1,6 +1,6 @@
 """Build property of the K3 scalar passes, checked where nvcc cross-compiles (no GPU): with the team helpers shared
-(MLRN_SHARED_HELPERS, team.cuh) no k_pass kernel is larger than 9 k instructions and the helpers exist as functions of
-their own.  Inlined, the TDE kernel was 13.3 k instructions (213 KB) and ran 2.1x slower."""
+(MLRN_SHARED_HELPERS, team.cuh) no k_pass kernel is larger than 9 k instructions (a kernel's count includes its copy of
+every helper it calls: ptxas places called device functions inside the calling kernel's code).  Inlined, the TDE kernel was 13.3 k instructions (213 KB) and ran 2.1x slower."""
 import os
 import re
 import shutil
@@ -38,8 +38,5 @@ def test_k3_kernels_keep_their_code_size(tmp_path):
     kernels = {k: v for k, v in fns.items() if "k_pass" in k}
     assert len(kernels) == 4, sorted(fns)
     assert max(kernels.values()) <= 9000, kernels                 # 16 B each; the inlined TDE kernel was 13.3 k (213 KB)
-    helpers = [k for k in fns if "k_pass" not in k]
-    for piece in ("team_polyfit1", "team_sum", "team_log10", "paired_series"):
-        assert any(piece in h for h in helpers), (piece, helpers)
     frames = [int(x) for x in re.findall(r"(\d+) bytes stack frame", log.stderr)]
     assert frames and max(frames) <= 256, frames
