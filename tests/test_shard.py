@@ -150,3 +150,50 @@ def test_batch_ranges_cover_every_object_once_with_equal_batch_counts():
     import pytest
     with pytest.raises(ValueError):
         batch_ranges([(0, 4)], 0)
+
+
+def _batched_worker(rank, world, port, n_total, per_batch, q):
+    """The bench's C5 plan on gloo: batch j on every rank, then the all-gather of batch j's rows into block j."""
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mallorn_astrophysics_b200.shard import allgather_table, batch_ranges, equal_ranges
+    sub = batch_ranges(equal_ranges(n_total, world), per_batch)
+    blocks = []
+    for j in range(len(sub[0])):
+        rows = [sub[r][j][1] - sub[r][j][0] for r in range(world)]
+        lo, hi = sub[rank][j]
+        local = torch.zeros((hi - lo, 3), dtype=torch.float64)
+        local[:, 0] = torch.arange(lo, hi, dtype=torch.float64)          # the object a row belongs to
+        local[:, 1] = rank
+        local[:, 2] = j
+        out = torch.empty((world * max(rows), 3), dtype=torch.float64) if max(rows) else None
+        blocks.append(allgather_table(local, rows, out=out).numpy())
+    q.put((rank, blocks, sub))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total,per_batch", [(40, 5), (37, 4)])
+def test_batched_plan_world2_gloo(n_total, per_batch):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_batched_worker, args=(r, 2, port, n_total, per_batch, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = {r: (b, s) for r, b, s in (q.get(timeout=120) for _ in range(2))}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    blocks0, sub = got[0]
+    blocks1, _ = got[1]
+    seen = []
+    for j, (b0, b1) in enumerate(zip(blocks0, blocks1)):
+        assert np.array_equal(b0, b1)                                   # every rank holds the same block
+        want = np.concatenate([np.arange(*sub[r][j]) for r in range(2)])   # block j = [rank 0's batch j | rank 1's batch j]
+        assert np.array_equal(b0[:, 0], want) and (b0[:, 2] == j).all()
+        seen.append(b0[:, 0])
+    assert np.array_equal(np.sort(np.concatenate(seen)), np.arange(n_total))    # the set, every object once
