@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256, 2) k_gp1d(const long long* __restrict__ s
 
 int run_gp1d(const mlrn_store* s, double* out_dev, int* status_dev, cudaStream_t st) {
   if (s->n_obj == 0) return MLRN_OK;
-  const int longest = s->max_seg > 5 ? s->max_seg : 5;
+  const int longest = s->max_seg > GP1D_MAX_POINTS ? GP1D_MAX_POINTS : (s->max_seg > 5 ? s->max_seg : 5);      // longer bands are not fitted (gp1d.cuh)
   int cap = longest < 52 ? longest : 52;                      // 52 points: 15 KB per warp
   if (const char* e = getenv("MLRN_GP1D_CAP")) { int v = atoi(e); if (v >= 5 && v <= 160) cap = v < longest ? v : longest; }
   const size_t per_warp = gp1d_warp_bytes(cap);

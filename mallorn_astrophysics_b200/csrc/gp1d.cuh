@@ -26,7 +26,11 @@ constexpr int GP1D_STATUS = 12;        // per object: per band {evaluations (all
 
 MLRN_FN_FORCE int tri_size(int n) { return n * (n + 1) / 2; }          // packed lower triangle of an n x n matrix
 // scratch doubles one team needs for a band of n valid points: matrix of order n+1, x, y, alpha, v, w, pivots
-MLRN_HD int gp1d_scratch_doubles(int n) { return (n + 1) * (n + 2) / 2 + 6 * (n + 1); }
+MLRN_HD long long gp1d_scratch_doubles(int n) { return (long long)(n + 1) * (n + 2) / 2 + 6LL * (n + 1); }
+// Longest band the per-band GP fits: the packed triangle is indexed with 32-bit integers (tri_size(n + 1) must fit) and
+// a 32,768-point band already needs a 4.3 GB matrix (sklearn's dense one would be 8.6 GB).  Longer bands are reported
+// like bands with fewer than 5 points: not fitted, their columns NaN (documented deviation; survey bands have ~25 points).
+constexpr int GP1D_MAX_POINTS = 32768;
 
 struct Gp1dScratch {
   double* A;        // packed lower triangle, order n+1
@@ -140,7 +144,7 @@ struct Gp1dBandResult { double length_scale, amplitude, noise, loglik; int nfev,
 template <class Team>
 MLRN_FN int gp1d_prepare(const Team& tm, const double* gt, const double* gf, const double* ge, int n_raw,
                          double* sx, double* sy, double* sal, double& t_range, double& f_std) {
-  if (n_raw < 5) return 0;
+  if (n_raw < 5 || n_raw > GP1D_MAX_POINTS) return 0;
   // keep rows with finite flux, finite error, error > 0 (:58); order preserved
   int n = 0;
   for (int base = 0; base < n_raw; base += Team::size) {

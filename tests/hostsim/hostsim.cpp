@@ -161,7 +161,13 @@ int hs_gp1d(long long n_obj, const long long* seg_off, const double* t, const do
             const unsigned short* rank, double* out, int* status) {
   HostTeam tm;
   const int bands[4] = {BG, BR, BI, BZ};
-  std::vector<double> scratch(gp1d_scratch_doubles(MAX_OBS));
+  int longest = 5;                                   // scratch for the longest band that will be fitted
+  for (long long o = 0; o < n_obj; ++o)
+    for (int j = 0; j < 4; ++j) {
+      const int n = (int)(seg_off[o * N_SEG + bands[j] + 1] - seg_off[o * N_SEG + bands[j]]);
+      if (n > longest && n <= GP1D_MAX_POINTS) longest = n;
+    }
+  std::vector<double> scratch((size_t)gp1d_scratch_doubles(longest));
   LbfgsB<3> opt; double ctl[8];
   for (long long o = 0; o < n_obj; ++o) {
     Gp1dBandResult res[4];
